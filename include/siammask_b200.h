@@ -1,0 +1,117 @@
+/* siammask_b200 — C ABI of the B200-native SiamMask per-frame inference hot path.
+ *
+ * The reference (foolwood/SiamMask) has no FFI for this path: the boundary is the duck-typed Python
+ * object `state['net']` used by tools/test.py (siamese_init :155, siamese_track :201,203,257).  The entry
+ * points below are what a binding for that object needs; each cites the reference method it replaces.
+ * `siammask_b200/custom.py` is the ctypes binding that restores the Python API on top of them
+ * (see INTEGRATION.md).
+ *
+ * Conventions: plain pointers and sizes only.  All *device* pointers are fp32 NCHW exactly as the
+ * reference exchanges them (tools/test.py:61-64,205-206); the caller owns every I/O buffer, the engine
+ * owns weights, workspace and per-slot caches.  Work is enqueued on `stream` (a cudaStream_t passed as
+ * void*) and returns without synchronising.  Return value 0 = ok, negative = error with the message in
+ * sm_last_error() (thread local).  Nothing here ever falls back to a CPU implementation: without a
+ * CUDA device every compute entry point fails with an error.
+ */
+#ifndef SIAMMASK_B200_H
+#define SIAMMASK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sm_engine sm_engine;
+
+enum { SM_PRECISION_EXACT = 0, /* fp16 hi+lo operands, 3 tensor-core MMAs per k-step: fp32-class results */
+       SM_PRECISION_FAST = 1   /* single fp16 MMA per k-step */ };
+enum { SM_BACKEND_TENSOR = 0,  /* tcgen05 implicit-GEMM convolutions */
+       SM_BACKEND_SIMT = 1     /* CUDA-core reference convolutions (debug / bisecting only) */ };
+enum { SM_TRACK_MASK_FEATURES = 1, /* keep p0/p1/p2 + mask corr feature for sm_refine (track_mask) */
+       SM_TRACK_MASK_HEAD = 2      /* also evaluate the 256->3969 mask head (dead under --refine) */ };
+
+typedef struct sm_config {
+  int32_t search_size;   /* hp.instance_size: 255 (config_davis.json) or e.g. 383 */
+  int32_t max_batch;     /* largest B passed to sm_track / sm_template */
+  int32_t num_slots;     /* tracker streams whose template kernels stay cached on the device */
+  int32_t precision;     /* SM_PRECISION_* */
+  int32_t backend;       /* SM_BACKEND_* */
+  int32_t anchor_num;    /* len(ratios)*len(scales), models/siammask_sharp.py:17 (5) */
+  int32_t with_mask;     /* build mask_model + refine_model (siammask_sharp) or RPN only (siamrpn_resnet) */
+} sm_config;
+
+/* One checkpoint tensor: reference state-dict name, host fp32 data, shape. */
+typedef struct sm_tensor_desc {
+  const char* name;
+  const float* data;
+  int32_t ndim;
+  int64_t shape[4];
+} sm_tensor_desc;
+
+/* Custom.__init__ — experiments/siammask_sharp/custom.py:162-168 */
+int sm_engine_create(const sm_config* cfg, sm_engine** out);
+void sm_engine_destroy(sm_engine* e);
+
+/* load_pretrain + model.load_state_dict — utils/load_helper.py:30-54.  Folds eval-mode BatchNorm
+ * (eps 1e-5) into the convolutions, repacks to the kernels' layouts and uploads.  Copies; the caller
+ * keeps ownership of `tensors`. */
+int sm_engine_load_weights(sm_engine* e, const sm_tensor_desc* tensors, int32_t n);
+
+/* The packed device weight arena (layout is a pure function of sm_config).  Multi-GPU init: rank 0
+ * calls sm_engine_load_weights, every rank broadcasts [ptr, ptr+bytes) with NCCL, the other ranks
+ * call sm_engine_adopt_weights. */
+int sm_engine_weight_blob(sm_engine* e, void** dev_ptr, size_t* bytes);
+int sm_engine_adopt_weights(sm_engine* e);
+
+/* Custom.template — custom.py:173-174.  z: device f32 [B,3,127,127].  Caches, for slots
+ * slot0..slot0+B-1, the template feature and the three conv_kernel outputs (models/rpn.py:64),
+ * which the reference recomputes every frame. */
+int sm_template(sm_engine* e, int32_t slot0, int32_t B, const float* z_nchw, void* stream);
+
+/* Custom.track / Custom.track_mask — custom.py:176-186.  x: device f32 [B,3,S,S] paired with slots
+ * slot0..slot0+B-1.  cls: f32 [B,2A,R,R], loc: f32 [B,4A,R,R], mask: f32 [B,3969,R,R] or NULL.
+ * flags: SM_TRACK_*. */
+int sm_track(sm_engine* e, int32_t slot0, int32_t B, const float* x_nchw, float* cls, float* loc, float* mask,
+             int32_t flags, void* stream);
+
+/* Custom.track_refine — custom.py:188-190 -> Refine.forward(test=True) :131-154.  pos: device int32 [B,2]
+ * (dy,dx) per stream; out: device f32 [B,127*127].  Uses the features cached by the preceding
+ * sm_track(..., SM_TRACK_MASK_FEATURES) with the same B. */
+int sm_refine(sm_engine* e, int32_t B, const int32_t* pos, float* out, void* stream);
+
+/* Whole step through HOST buffers (pinned recommended): H2D of x, track(+mask features), optional refine,
+ * D2H of cls / loc / refine logits, then stream synchronise.  mask_out_host may be NULL (no refine). */
+int sm_track_host(sm_engine* e, int32_t slot0, int32_t B, const float* x_host, float* cls_host, float* loc_host,
+                  const int32_t* pos_host, float* mask_out_host, void* stream);
+
+/* conv2d_dw_group — models/rpn.py:32-38, standalone: x f32 [B,C,H,W], k f32 [B,C,kh,kw] ->
+ * out f32 [B,C,H-kh+1,W-kw+1], all device pointers. */
+int sm_xcorr_depthwise(const float* x, const float* k, float* out, int32_t B, int32_t C, int32_t H, int32_t W,
+                       int32_t kh, int32_t kw, void* stream);
+
+/* F.conv2d + folded affine (+ReLU) as a standalone operator, used by the kernel-level parity tests:
+ * x f32 NCHW [B,Cin,H,W], w f32 [Cout,Cin,KH,KW], scale/shift f32 [Cout] (may be NULL), out f32 NCHW.
+ * backend/precision as in sm_config. */
+int sm_conv2d(const float* x, const float* w, const float* scale, const float* shift, float* out, int32_t B,
+              int32_t Cin, int32_t H, int32_t W, int32_t Cout, int32_t KH, int32_t KW, int32_t stride, int32_t pad,
+              int32_t dil, int32_t relu, int32_t backend, int32_t precision, void* stream);
+
+/* Copies a cached intermediate of the last sm_template / sm_track as f32 NCHW (parity checks):
+ * "p0","p1","p2","p3","search","corr_cls","corr_loc","corr_mask","zf".  shape4 receives [B,C,H,W];
+ * with out == NULL only the shape is returned. */
+int sm_export(sm_engine* e, const char* what, float* out, int64_t* shape4, void* stream);
+
+/* Number of kernel launches the engine has issued since creation (bench.py reports it). */
+int64_t sm_launch_count(const sm_engine* e);
+/* Device bytes held by the engine (weights + workspace + caches). */
+size_t sm_engine_bytes(const sm_engine* e);
+
+const char* sm_last_error(void);
+const char* sm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIAMMASK_B200_H */

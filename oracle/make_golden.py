@@ -1,0 +1,77 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference model (imported read-only from
+/root/reference) on the seeded, calibrated checkpoint.  TEST INFRASTRUCTURE ONLY; run in the build
+container (the reference does not travel to the GPU box):
+
+    python -m oracle.make_golden
+
+The reference has no golden vectors of its own; these files pin `oracle/siammask_oracle.py`
+to the reference implementation itself."""
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+REF = os.environ.get("SIAMMASK_REFERENCE", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+MASK_CH = slice(0, 3969, 97)      # 41 of the 3969 mask-head channels (the full tensor is 9.9 MB)
+ANCHORS = {"stride": 8, "ratios": [0.33, 0.5, 1, 2, 3], "scales": [8], "round_dight": 0}
+
+
+def reference_model(sd):
+    sys.path[:0] = [REF, os.path.join(REF, "experiments", "siammask_sharp")]
+    from custom import Custom  # noqa: the reference's own class
+    m = Custom(anchors=ANCHORS).eval()
+    m.load_state_dict(sd, strict=False)
+    return m
+
+
+def sub(t, step):
+    return t.flatten()[::step].numpy().copy()
+
+
+def main():
+    from oracle.calibrate import calibrated_state_dict, synthetic_inputs
+    warnings.filterwarnings("ignore")
+    torch.set_num_threads(8)
+    sd = calibrated_state_dict(0)
+    m = reference_model(sd)
+    os.makedirs(OUT, exist_ok=True)
+    with torch.no_grad():
+        # --- config 1: B=1, search 255
+        z, x = synthetic_inputs(1, 1)
+        m.template(z)
+        cls, loc, mask = m.track_mask(x)
+        feats = {f"p{i}": sub(f, 257) for i, f in enumerate(m.feature)}
+        r1 = m.track_refine((12, 12))
+        r2 = m.track_refine((3, 20))
+        np.savez_compressed(os.path.join(OUT, "sharp_b1_s255.npz"), cls=cls.numpy(), loc=loc.numpy(),
+                            mask_sub=mask[:, MASK_CH].numpy(), refine_12_12=r1.numpy(), refine_3_20=r2.numpy(),
+                            zf=m.zf.numpy(), search=sub(m.search, 7), corr=sub(m.corr_feature, 7), **feats)
+        # --- paired batch B=2 (the reference's batched semantics), track only
+        z2, x2 = synthetic_inputs(2, 2)
+        m.template(z2)
+        cls2, loc2 = m.track(x2)
+        np.savez_compressed(os.path.join(OUT, "rpn_b2_s255.npz"), cls=cls2.numpy(), loc=loc2.numpy())
+        # --- large search 383 -> 41x41 response
+        z3, x3 = synthetic_inputs(3, 1, search=383)
+        m.template(z3)
+        cls3, loc3 = m.track(x3)
+        np.savez_compressed(os.path.join(OUT, "rpn_b1_s383.npz"), cls=cls3.numpy(), loc=loc3.numpy())
+        # --- standalone depthwise xcorr (models/rpn.py:32-38)
+        sys.path[:0] = [REF]
+        from models.rpn import conv2d_dw_group
+        g = torch.Generator().manual_seed(7)
+        xs = torch.randn(2, 8, 29, 29, generator=g)
+        ks = torch.randn(2, 8, 5, 5, generator=g)
+        np.savez_compressed(os.path.join(OUT, "xcorr_small.npz"), x=xs.numpy(), k=ks.numpy(),
+                            out=conv2d_dw_group(xs, ks).numpy())
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,105 @@
+// Shared types for the SiamMask hot-path kernels (sm_100a).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace smk {
+
+// NHWC activation.  Exact precision mode keeps every activation as two fp16 planes,
+// value = hi + lo (22 significant bits); fast mode uses the hi plane only (lo == nullptr).
+struct Act {
+  __half* hi = nullptr;
+  __half* lo = nullptr;
+  int B = 0, H = 0, W = 0, C = 0;
+  __host__ __device__ size_t numel() const { return (size_t)B * H * W * C; }
+  __host__ __device__ int M() const { return B * H * W; }
+};
+
+struct ConvGeom {
+  int Cin, Cout, KH, KW, stride, pad, dil;
+  __host__ __device__ int out_size(int in) const { return (in + 2 * pad - dil * (KH - 1) - 1) / stride + 1; }
+};
+
+enum OutMode : int { OUT_NHWC_SPLIT = 0, OUT_NHWC_F32 = 1, OUT_NCHW_F32 = 2 };
+
+// Epilogue common to the tensor-core GEMM conv and the SIMT reference conv:
+//   v = acc * alpha[c] + beta[c]  (+ residual[m][c])  (relu)  -> out
+struct Epilogue {
+  const float* alpha = nullptr;   // [Cout] (folded BN scale / pow2 weight de-scaling)
+  const float* beta = nullptr;    // [Cout] (folded BN shift or conv bias)
+  const __half* res_hi = nullptr; // residual NHWC [M][Cout], split planes
+  const __half* res_lo = nullptr;
+  __half* out_hi = nullptr;       // OUT_NHWC_SPLIT
+  __half* out_lo = nullptr;
+  float* out_f32 = nullptr;       // OUT_NHWC_F32 / OUT_NCHW_F32
+  int out_mode = OUT_NHWC_SPLIT;
+  int relu = 0;
+};
+
+// Parameters of the tcgen05 implicit-GEMM convolution kernel (passed by value, __grid_constant__).
+struct GemmParams {
+  CUtensorMap tmA[2];  // activations: hi / lo plane.  a_mode 0: 2D [M][Cin]; 1: im2col over NHWC
+  CUtensorMap tmB[2];  // weights: hi / lo, 2D [Cout_pad][Ktot], K-major
+  int M, Cout, Ho, Wo;
+  int num_kb, cblks, KW;
+  int stride, pad, dil;
+  int a_mode;
+  int n_tiles, m_tiles;
+  Epilogue ep;
+};
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define SMK_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      throw smk::CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " +    \
+                           __FILE__ + ":" + std::to_string(__LINE__));                              \
+  } while (0)
+
+#define SMK_CHECK(cond, msg)                                                                        \
+  do {                                                                                              \
+    if (!(cond)) throw std::runtime_error(std::string("check failed: ") + #cond + " — " + (msg));   \
+  } while (0)
+
+// ---- launchers (defined in the .cu files) ---------------------------------------------------
+
+// conv_gemm_sm100.cu : tensor-core implicit GEMM. nsplit = 1 (fast) or 2 planes (exact, 3 MMAs).
+bool gemm_conv_supported(const ConvGeom& g);
+void launch_gemm_conv(const Act& in, const ConvGeom& g, const __half* w_hi, const __half* w_lo, int cout_pad,
+                      const Epilogue& ep, int nsplit, int num_sms, cudaStream_t st);
+
+// simt_kernels.cu
+void launch_ref_conv(const Act& in, const ConvGeom& g, const float* w_krsc_cout, const Epilogue& ep,
+                     cudaStream_t st);
+void launch_stem(const float* x_nchw, int B, int S, const float* w, const float* alpha, const float* beta, Act out,
+                 cudaStream_t st);
+void launch_maxpool3s2(const Act& in, Act out, cudaStream_t st);
+void launch_xcorr_nhwc(const Act& x, const __half* k_hi, const __half* k_lo, int kh, int kw, Act out,
+                       cudaStream_t st);
+void launch_xcorr_nchw_f32(const float* x, const float* k, float* out, int planes, int H, int W, int kh, int kw,
+                           cudaStream_t st);
+void launch_crop_center(const Act& in, int crop, Act out, cudaStream_t st);
+void launch_refine_crop(const Act& in, const int32_t* pos, int scale, int padv, int size, Act out, cudaStream_t st);
+void launch_gather_corr(const Act& corr, const int32_t* pos, float* out, cudaStream_t st);
+void launch_deconv(const float* p3, const float* w, const float* bias, float* out, int B, int Cin, int N,
+                   int cout, cudaStream_t st);
+void launch_split_to_f32(const Act& in, float* out, cudaStream_t st);
+void launch_import_nchw(const float* x_nchw, Act out, cudaStream_t st);
+// small-channel fp32 NHWC 3x3 pad-1 conv: in = up(a (+ b)); ymap/xmap: device nearest-upsample source indices
+void launch_small_conv3x3_maps(const float* a, const float* b, int B, int Hi, int Wi, int Ho, int Wo, int Cin, int Cout,
+                               const int* ymap, const int* xmap, const float* w, const float* bias, int relu,
+                               float* out, cudaStream_t st);
+std::vector<int> nearest_index_table(int out_size, int in_size);
+int gemm_cout_pad(int cout);
+
+}  // namespace smk

@@ -1,0 +1,429 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05) for sm_100a.
+//
+//   out[m][n] = epilogue( sum_k A[m][k] * W[n][k] ),  m = (b, ho, wo) flattened, k = (r, s, c) with c fastest.
+//
+// * A (NHWC fp16 activation planes) is staged by TMA: plain 2-D tiles for 1x1/stride-1 convs, im2col-mode
+//   tiles (cp.async.bulk.tensor.4d...im2col) for everything else — padding, stride and dilation are resolved
+//   by the TMA unit, out-of-image taps arrive as zeros, and the 128-pixel M tile runs across row and image
+//   boundaries so batch absorbs the odd spatial sizes (31x31, 29x29, 25x25 ...).
+// * W (K-major fp16, [Cout_pad][KH*KW*Cin]) is staged by 2-D TMA tiles.  Both land in 128B-swizzled smem
+//   and are consumed by tcgen05.mma (M=128, N=BLOCK_N, K=16) issued by a single thread; accumulators live
+//   in TMEM, double-buffered so the epilogue of tile i overlaps the main loop of tile i+1.
+// * Precision: NSPLIT=1 multiplies the fp16 hi planes only.  NSPLIT=2 ("exact") keeps activations and
+//   weights as hi+lo fp16 pairs (22 significant bits) and issues three MMAs per k-step
+//   (hi*hi + lo*hi + hi*lo) into the same fp32 accumulator — fp32-class results from the fp16 tensor pipe.
+// * Epilogue (4 warps, one TMEM lane quarter each): acc*alpha[c]+beta[c] (+residual) (ReLU) written as
+//   NHWC split-fp16 planes, NHWC fp32, or NCHW fp32 (the boundary layout of the reference's outputs,
+//   tools/test.py:205-206) — TMEM lanes are pixels, so NCHW stores are coalesced across the warp.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one lane),
+// warps 2..5 = epilogue.  Persistent: grid = min(tiles, SMs), static round-robin over (m_tile, n_tile).
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <mutex>
+
+namespace smk {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 fp16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int NUM_THREADS = 192;
+
+template <int BLOCK_N, int NSPLIT>
+struct Cfg {
+  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = NSPLIT * (A_TILE_BYTES + B_TILE_BYTES);
+  static constexpr int RAW_STAGES = (SMEM_LIMIT - 2048) / STAGE_BYTES;
+  static constexpr int STAGES = RAW_STAGES > 6 ? 6 : RAW_STAGES;
+  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                   : (2 * BLOCK_N <= 256) ? 256 : 512;
+  static constexpr int CH = BLOCK_N < 32 ? 16 : 32;   // epilogue column chunk
+  // one CTA per SM: keep the request above half of the SM's shared memory
+  static constexpr int SMEM_BYTES_RAW = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = SMEM_BYTES_RAW < 120 * 1024 ? 120 * 1024 : SMEM_BYTES_RAW;
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N constraint for M=128");
+  static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget");
+};
+
+template <int CH>
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CH]) {
+  if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr, r);
+  else tmem_ld_32x32b_x16(taddr, r);
+}
+
+template <int BLOCK_N, int NSPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
+  using C = Cfg<BLOCK_N, NSPLIT>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int CH = C::CH;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSPLIT; ++i) {
+      tma_prefetch_desc(&p.tmA[i]);
+      tma_prefetch_desc(&p.tmB[i]);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);   // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.n_tiles) * BLOCK_M;
+      const int n0 = (tile % p.n_tiles) * BLOCK_N;
+      int wb = 0, hb = 0, nb = 0;
+      if (p.a_mode == 1) {
+        const int q = m0 % p.Wo;
+        const int t = m0 / p.Wo;
+        wb = q * p.stride - p.pad;
+        hb = (t % p.Ho) * p.stride - p.pad;
+        nb = t / p.Ho;
+      }
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + stage * C::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+        const int tap = kb / p.cblks;
+        const int c0 = (kb - tap * p.cblks) * BLOCK_K;
+#pragma unroll
+        for (int s = 0; s < NSPLIT; ++s) {
+          uint8_t* a_dst = st + s * A_TILE_BYTES;
+          if (p.a_mode == 0) {
+            tma_load_2d(a_dst, &p.tmA[s], &full_bar[stage], c0, m0);
+          } else {
+            const int r = tap / p.KW;
+            const int sx = tap - r * p.KW;
+            tma_load_im2col_4d(a_dst, &p.tmA[s], &full_bar[stage], c0, wb, hb, nb,
+                               static_cast<uint16_t>(sx * p.dil), static_cast<uint16_t>(r * p.dil));
+          }
+          uint8_t* b_dst = st + NSPLIT * A_TILE_BYTES + s * C::B_TILE_BYTES;
+          tma_load_2d(b_dst, &p.tmB[s], &full_bar[stage], kb * BLOCK_K, n0);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (threadIdx.x == 32) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_f16(BLOCK_M, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
+        const uint32_t b_hi = a_hi + NSPLIT * A_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          const uint32_t koff = k * UMMA_K * 2;   // bytes along K inside the 128B swizzle row
+          const uint64_t da_hi = umma_desc_kmajor_sw128(a_hi + koff);
+          const uint64_t db_hi = umma_desc_kmajor_sw128(b_hi + koff);
+          umma_f16(tmem_d, da_hi, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+          if constexpr (NSPLIT == 2) {
+            const uint64_t da_lo = umma_desc_kmajor_sw128(a_hi + A_TILE_BYTES + koff);
+            const uint64_t db_lo = umma_desc_kmajor_sw128(b_hi + C::B_TILE_BYTES + koff);
+            umma_f16(tmem_d, da_lo, db_hi, idesc, 1u);
+            umma_f16(tmem_d, da_hi, db_lo, idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
+        if (kb == p.num_kb - 1) umma_commit(&tfull_bar[acc]); // accumulator complete
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 2) {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const Epilogue& ep = p.ep;
+    const int HoWo = p.Ho * p.Wo;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / p.n_tiles) * BLOCK_M;
+      const int n0 = (tile % p.n_tiles) * BLOCK_N;
+      const int m = m0 + quarter * 32 + lane;
+      const bool row_ok = m < p.M;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+        uint32_t r[CH];
+        tmem_ld_chunk<CH>(taddr + c0, r);
+        tmem_ld_wait();
+        const int n = n0 + c0;
+        float v[CH];
+#pragma unroll
+        for (int j = 0; j < CH; j += 4) {
+          const float4 al = __ldg(reinterpret_cast<const float4*>(ep.alpha + n + j));
+          const float4 be = __ldg(reinterpret_cast<const float4*>(ep.beta + n + j));
+          v[j + 0] = fmaf(__uint_as_float(r[j + 0]), al.x, be.x);
+          v[j + 1] = fmaf(__uint_as_float(r[j + 1]), al.y, be.y);
+          v[j + 2] = fmaf(__uint_as_float(r[j + 2]), al.z, be.z);
+          v[j + 3] = fmaf(__uint_as_float(r[j + 3]), al.w, be.w);
+        }
+        if (row_ok) {
+          if (ep.res_hi != nullptr) {
+            const size_t off = static_cast<size_t>(m) * p.Cout + n;
+#pragma unroll
+            for (int j = 0; j < CH; j += 8) {
+              const uint4 h = *reinterpret_cast<const uint4*>(ep.res_hi + off + j);
+              const __half2* hh = reinterpret_cast<const __half2*>(&h);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 f = __half22float2(hh[t]);
+                v[j + 2 * t] += f.x;
+                v[j + 2 * t + 1] += f.y;
+              }
+              if (ep.res_lo != nullptr) {
+                const uint4 l = *reinterpret_cast<const uint4*>(ep.res_lo + off + j);
+                const __half2* ll = reinterpret_cast<const __half2*>(&l);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float2 f = __half22float2(ll[t]);
+                  v[j + 2 * t] += f.x;
+                  v[j + 2 * t + 1] += f.y;
+                }
+              }
+            }
+          }
+          if (ep.relu) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (ep.out_mode == OUT_NHWC_SPLIT) {
+            const size_t off = static_cast<size_t>(m) * p.Cout + n;
+#pragma unroll
+            for (int j = 0; j < CH; j += 8) {
+              uint4 h, l;
+              __half2* hh = reinterpret_cast<__half2*>(&h);
+              __half2* ll = reinterpret_cast<__half2*>(&l);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const __half2 hv = __floats2half2_rn(v[j + 2 * t], v[j + 2 * t + 1]);
+                hh[t] = hv;
+                const float2 hf = __half22float2(hv);
+                ll[t] = __floats2half2_rn(v[j + 2 * t] - hf.x, v[j + 2 * t + 1] - hf.y);
+              }
+              *reinterpret_cast<uint4*>(ep.out_hi + off + j) = h;
+              if (ep.out_lo != nullptr) *reinterpret_cast<uint4*>(ep.out_lo + off + j) = l;
+            }
+          } else if (ep.out_mode == OUT_NHWC_F32) {
+            float* dst = ep.out_f32 + static_cast<size_t>(m) * p.Cout + n;
+#pragma unroll
+            for (int j = 0; j < CH; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {  // OUT_NCHW_F32: lanes are consecutive pixels of one image plane -> coalesced
+            const int b = m / HoWo;
+            const int hw = m - b * HoWo;
+            float* dst = ep.out_f32 + (static_cast<size_t>(b) * p.Cout + n) * HoWo + hw;
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (n + j < p.Cout) dst[static_cast<size_t>(j) * HoWo] = v[j];
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ host side: tensor maps
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+using EncodeIm2colFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct DriverApi {
+  EncodeTiledFn tiled = nullptr;
+  EncodeIm2colFn im2col = nullptr;
+  int driver_version = 0;
+};
+
+// The driver entry points are resolved at run time so the library has no link-time libcuda
+// dependency (it must load on a box without a GPU driver for the symbol-export test).
+const DriverApi& driver_api() {
+  static DriverApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    SMK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    SMK_CHECK(fn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    api.tiled = reinterpret_cast<EncodeTiledFn>(fn);
+    fn = nullptr;
+    SMK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q));
+    SMK_CHECK(fn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeIm2col not available");
+    api.im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+    SMK_CUDA(cudaDriverGetVersion(&api.driver_version));
+  });
+  return api;
+}
+
+CUtensorMap make_map_2d(const __half* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * sizeof(__half)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = driver_api().tiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides,
+                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SMK_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed, code " + std::to_string((int)r));
+  return m;
+}
+
+CUtensorMap make_map_im2col(const __half* base, const Act& in, const ConvGeom& g) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.B};
+  cuuint64_t strides[3] = {(cuuint64_t)in.C * 2, (cuuint64_t)in.W * in.C * 2, (cuuint64_t)in.H * in.W * in.C * 2};
+  // fprop corners (cutlass/conv/collective/detail.hpp compute_{lower,upper}_corner_whd):
+  //   lower = -pad, upper = pad - (k-1)*dilation; base pixel = lower + q*stride, tap offset = s*dilation.
+  int lower[2] = {-g.pad, -g.pad};
+  int upper[2] = {g.pad - (g.KW - 1) * g.dil, g.pad - (g.KH - 1) * g.dil};
+  cuuint32_t estr[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
+  const DriverApi& api = driver_api();
+  CUresult r = api.im2col(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), dims, strides, lower,
+                          upper, BLOCK_K, BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SMK_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed, code " + std::to_string((int)r));
+  // Same small-tensor descriptor fix-up CuTe applies for drivers <= 13.1
+  // (cute/atom/copy_traits_sm90_im2col.hpp, make_im2col_tma_copy_desc).
+  if (api.driver_version <= 13010 && in.numel() * sizeof(__half) < 131072)
+    reinterpret_cast<uint64_t*>(&m)[1] &= ~(1ull << 21);
+  return m;
+}
+
+template <int BLOCK_N, int NSPLIT>
+void launch_cfg(const GemmParams& p, int num_sms, cudaStream_t st) {
+  using C = Cfg<BLOCK_N, NSPLIT>;
+  auto kern = conv_gemm_kernel<BLOCK_N, NSPLIT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);
+  SMK_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+bool gemm_conv_supported(const ConvGeom& g) { return g.Cin % BLOCK_K == 0 && g.Cout >= 1; }
+
+int gemm_cout_pad(int cout) {
+  if (cout <= 16) return 16;
+  if (cout <= 32) return 32;
+  if (cout <= 64) return 64;
+  if (cout <= 128) return 128;
+  return (cout + 255) / 256 * 256;
+}
+
+void launch_gemm_conv(const Act& in, const ConvGeom& g, const __half* w_hi, const __half* w_lo, int cout_pad,
+                      const Epilogue& ep, int nsplit, int num_sms, cudaStream_t st) {
+  SMK_CHECK(gemm_conv_supported(g), "Cin must be a multiple of 64 for the tensor-core conv");
+  SMK_CHECK(in.C == g.Cin, "input channels mismatch");
+  SMK_CHECK(nsplit == 1 || (in.lo != nullptr && w_lo != nullptr), "exact mode needs lo planes");
+  const int Ho = g.out_size(in.H), Wo = g.out_size(in.W);
+  GemmParams p;
+  p.M = in.B * Ho * Wo;
+  p.Cout = g.Cout;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.cblks = g.Cin / BLOCK_K;
+  p.num_kb = g.KH * g.KW * p.cblks;
+  p.KW = g.KW;
+  p.stride = g.stride;
+  p.pad = g.pad;
+  p.dil = g.dil;
+  p.a_mode = (g.KH == 1 && g.KW == 1 && g.stride == 1 && g.pad == 0) ? 0 : 1;
+  const int block_n = cout_pad < 256 ? cout_pad : (nsplit == 2 ? 128 : 256);
+  SMK_CHECK(cout_pad % block_n == 0, "cout_pad must be a multiple of the N tile");
+  if (ep.out_mode != OUT_NCHW_F32) SMK_CHECK(g.Cout == cout_pad, "NHWC outputs need Cout to match the padded tile width");
+  p.n_tiles = cout_pad / block_n;
+  p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  p.ep = ep;
+  const uint64_t ktot = (uint64_t)g.KH * g.KW * g.Cin;
+  for (int s = 0; s < nsplit; ++s) {
+    const __half* a = s == 0 ? in.hi : in.lo;
+    const __half* w = s == 0 ? w_hi : w_lo;
+    p.tmA[s] = p.a_mode == 0 ? make_map_2d(a, g.Cin, (uint64_t)in.M(), BLOCK_K, BLOCK_M) : make_map_im2col(a, in, g);
+    p.tmB[s] = make_map_2d(w, ktot, cout_pad, BLOCK_K, block_n);
+  }
+  if (nsplit == 1) { p.tmA[1] = p.tmA[0]; p.tmB[1] = p.tmB[0]; }
+
+#define SMK_DISPATCH(BN)                                             \
+  case BN:                                                           \
+    if (nsplit == 2) launch_cfg<BN, 2>(p, num_sms, st);              \
+    else launch_cfg<BN, 1>(p, num_sms, st);                          \
+    break;
+  switch (block_n) {
+    SMK_DISPATCH(16)
+    SMK_DISPATCH(32)
+    SMK_DISPATCH(64)
+    SMK_DISPATCH(128)
+    SMK_DISPATCH(256)
+    default: SMK_CHECK(false, "unsupported N tile");
+  }
+#undef SMK_DISPATCH
+}
+
+}  // namespace smk

@@ -1,0 +1,874 @@
+// Host side of the SiamMask hot path: weight ingest (BN fold, repack, fp16 split), the per-frame
+// schedule of kernels (backbone -> depthwise xcorr heads -> mask refine) and the C ABI
+// (include/siammask_b200.h).  Reference structure restated here:
+//   ResNet.forward / _make_layer          experiments/siammask_sharp/resnet.py:151-227
+//   ResDown / ResDownS / UP / MaskCorr    experiments/siammask_sharp/custom.py:12-96
+//   DepthCorr                             models/rpn.py:41-72
+//   Refine.forward(test=True)             experiments/siammask_sharp/custom.py:131-154
+//   Custom.template/track/track_mask/track_refine   custom.py:173-190
+#include "../../include/siammask_b200.h"
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <unordered_map>
+
+namespace smk {
+
+namespace {
+
+constexpr float BN_EPS = 1e-5f;
+constexpr size_t ALIGN = 256;
+inline size_t align_up(size_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
+
+thread_local std::string g_last_error;
+
+struct ConvW {
+  ConvGeom g{};
+  int cout_pad = 0;
+  bool gemm_ok = false;
+  std::string conv_key, bn_key;       // bn_key empty -> conv has a bias instead
+  size_t off_whi = 0, off_wlo = 0, off_wref = 0, off_alpha = 0, off_beta = 0;
+  __half* w_hi = nullptr;
+  __half* w_lo = nullptr;
+  float* w_ref = nullptr;
+  float* alpha = nullptr;             // pow2 de-scaling of the tensor-core weights
+  float* beta = nullptr;              // folded BN shift / conv bias
+};
+
+struct F32T {                         // fp32 NHWC tensor (refine stage)
+  float* p = nullptr;
+  int B = 0, H = 0, W = 0, C = 0;
+};
+
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t cap = 0, off = 0, peak = 0;
+  bool measure = false;
+  void reset() { off = 0; }
+  void* alloc(size_t bytes) {
+    off = align_up(off);
+    void* p = base + off;
+    off += bytes;
+    peak = std::max(peak, off);
+    if (!measure) SMK_CHECK(off <= cap, "workspace arena exhausted");
+    return p;
+  }
+};
+
+}  // namespace
+
+class Engine {
+ public:
+  explicit Engine(const sm_config& cfg);
+  ~Engine();
+
+  void load_weights(const sm_tensor_desc* t, int n);
+  void adopt_weights() { weights_ready_ = true; }
+  void weight_blob(void** p, size_t* bytes) { *p = blob_; *bytes = blob_bytes_; }
+
+  void do_template(int slot0, int B, const float* z, cudaStream_t st);
+  void do_track(int slot0, int B, const float* x, float* cls, float* loc, float* mask, int flags, cudaStream_t st);
+  void do_refine(int B, const int32_t* pos, float* out, cudaStream_t st);
+  void track_host(int slot0, int B, const float* xh, float* clsh, float* loch, const int32_t* posh, float* maskh,
+                  cudaStream_t st);
+  void do_export(const char* what, float* out, int64_t* shape4, cudaStream_t st);
+
+  int64_t launches() const { return launches_; }
+  size_t bytes() const { return total_bytes_; }
+  const sm_config& cfg() const { return cfg_; }
+
+ private:
+  // ---- construction
+  ConvW& add_layer(const std::string& conv_key, const std::string& bn_key, ConvGeom g);
+  void build_layer_table();
+  void assign_blob_layout();
+  size_t measure_arena(int B, int S, bool search);
+  // ---- packing
+  void pack_layer(ConvW& L, const std::map<std::string, const sm_tensor_desc*>& sd, uint8_t* host);
+  // ---- schedule
+  Act alloc_act(Arena& ar, int B, int H, int W, int C);
+  F32T alloc_f32(Arena& ar, int B, int H, int W, int C);
+  Act conv(const Act& in, const ConvW& L, bool relu, const Act* res, Arena& ar, cudaStream_t st);
+  void conv_into(const Act& in, const ConvW& L, Epilogue ep, cudaStream_t st);
+  F32T conv_f32(const Act& in, const ConvW& L, bool relu, Arena& ar, cudaStream_t st);
+  Act backbone(const float* x, int B, int S, Arena& ar, bool keep, cudaStream_t st);
+  F32T small(const F32T& a, const F32T* b, int Ho, const ConvW& L, bool relu, float* out_override, Arena& ar,
+             cudaStream_t st);
+  const ConvW& L(const std::string& k) const {
+    auto it = layers_.find(k);
+    SMK_CHECK(it != layers_.end(), "unknown layer " + k);
+    return it->second;
+  }
+  const int* updown_map(int out, int in) const {
+    auto it = maps_.find(out * 1000 + in);
+    SMK_CHECK(it != maps_.end(), "no upsample map");
+    return it->second;
+  }
+
+  sm_config cfg_;
+  bool exact_;
+  int num_sms_ = 148;
+  int R_ = 0;                          // response size (score_size)
+  std::map<std::string, ConvW> layers_;
+  std::vector<std::string> layer_order_;
+  size_t off_deconv_w_ = 0, off_deconv_b_ = 0, off_ones_ = 0;
+  float* deconv_w_ = nullptr;
+  float* deconv_b_ = nullptr;
+  float* ones_ = nullptr;              // alpha for the SIMT reference path (weights unscaled)
+  uint8_t* blob_ = nullptr;
+  size_t blob_bytes_ = 0;
+  bool weights_ready_ = false;
+
+  Arena search_arena_, templ_arena_, refine_arena_;
+  // per-slot template caches: [branch][slot][5][5][256] split planes, and zf for export
+  __half* kcache_hi_ = nullptr;
+  __half* kcache_lo_ = nullptr;
+  int n_branches_ = 2;
+  // host-path staging
+  float* stage_x_ = nullptr;
+  float* stage_cls_ = nullptr;
+  float* stage_loc_ = nullptr;
+  float* stage_mask_ = nullptr;
+  int32_t* stage_pos_ = nullptr;
+  int* maps_dev_ = nullptr;
+  std::map<int, const int*> maps_;
+
+  // state of the last track (Custom.feature / .search / .corr_feature, custom.py:182-184)
+  std::map<std::string, Act> named_;
+  int last_B_ = 0;
+  bool have_mask_feats_ = false;
+
+  int64_t launches_ = 0;
+  size_t total_bytes_ = 0;
+  bool measuring_ = false;
+};
+
+// ================================================================================================
+// construction
+
+ConvW& Engine::add_layer(const std::string& conv_key, const std::string& bn_key, ConvGeom g) {
+  ConvW w;
+  w.g = g;
+  w.conv_key = conv_key;
+  w.bn_key = bn_key;
+  w.gemm_ok = gemm_conv_supported(g);
+  w.cout_pad = w.gemm_ok ? gemm_cout_pad(g.Cout) : g.Cout;
+  layer_order_.push_back(conv_key);
+  return layers_[conv_key] = w;
+}
+
+void Engine::build_layer_table() {
+  const std::string F = "features.features.";
+  add_layer(F + "conv1", F + "bn1", {3, 64, 7, 7, 2, 0, 1});
+  struct LayerSpec { const char* name; int planes, blocks, stride, dilation; };
+  const LayerSpec specs[3] = {{"layer1", 64, 3, 1, 1}, {"layer2", 128, 4, 2, 1}, {"layer3", 256, 6, 1, 2}};
+  int inplanes = 64;
+  for (const auto& sp : specs) {
+    for (int i = 0; i < sp.blocks; ++i) {
+      const std::string P = F + sp.name + "." + std::to_string(i) + ".";
+      int stride = 1, dil = sp.dilation;
+      if (i == 0) {                       // _make_layer, resnet.py:184-215
+        stride = sp.stride;
+        dil = sp.dilation > 1 ? sp.dilation / 2 : 1;
+        ConvGeom ds;
+        if (sp.stride == 1 && sp.dilation == 1) ds = {inplanes, sp.planes * 4, 1, 1, 1, 0, 1};
+        else if (sp.dilation > 1) ds = {inplanes, sp.planes * 4, 3, 3, sp.stride, sp.dilation / 2, sp.dilation / 2};
+        else ds = {inplanes, sp.planes * 4, 3, 3, sp.stride, 0, 1};
+        add_layer(P + "downsample.0", P + "downsample.1", ds);
+      }
+      const int pad = dil > 1 ? dil : 2 - stride;   // Bottleneck.__init__, resnet.py:66-70
+      add_layer(P + "conv1", P + "bn1", {inplanes, sp.planes, 1, 1, 1, 0, 1});
+      add_layer(P + "conv2", P + "bn2", {sp.planes, sp.planes, 3, 3, stride, pad, dil});
+      add_layer(P + "conv3", P + "bn3", {sp.planes, sp.planes * 4, 1, 1, 1, 0, 1});
+      inplanes = sp.planes * 4;
+    }
+  }
+  add_layer("features.downsample.downsample.0", "features.downsample.downsample.1", {1024, 256, 1, 1, 1, 0, 1});
+  std::vector<std::pair<std::string, int>> heads = {{"rpn_model.cls.", 2 * cfg_.anchor_num},
+                                                    {"rpn_model.loc.", 4 * cfg_.anchor_num}};
+  if (cfg_.with_mask) heads.push_back({"mask_model.mask.", 63 * 63});
+  n_branches_ = (int)heads.size();
+  for (auto& h : heads) {
+    add_layer(h.first + "conv_kernel.0", h.first + "conv_kernel.1", {256, 256, 3, 3, 1, 0, 1});
+    add_layer(h.first + "conv_search.0", h.first + "conv_search.1", {256, 256, 3, 3, 1, 0, 1});
+    add_layer(h.first + "head.0", h.first + "head.1", {256, 256, 1, 1, 1, 0, 1});
+    add_layer(h.first + "head.3", "", {256, h.second, 1, 1, 1, 0, 1});
+  }
+  if (cfg_.with_mask) {
+    const std::string R = "refine_model.";
+    auto c3 = [&](const std::string& k, int ci, int co) { add_layer(R + k, "", {ci, co, 3, 3, 1, 1, 1}); };
+    c3("v0.0", 64, 16);  c3("v0.2", 16, 4);
+    c3("v1.0", 256, 64); c3("v1.2", 64, 16);
+    c3("v2.0", 512, 128); c3("v2.2", 128, 32);
+    c3("h2.0", 32, 32);  c3("h2.2", 32, 32);
+    c3("h1.0", 16, 16);  c3("h1.2", 16, 16);
+    c3("h0.0", 4, 4);    c3("h0.2", 4, 4);
+    c3("post0", 32, 16); c3("post1", 16, 4); c3("post2", 4, 1);
+  }
+}
+
+void Engine::assign_blob_layout() {
+  size_t off = 0;
+  for (const auto& k : layer_order_) {
+    ConvW& w = layers_[k];
+    const size_t K = (size_t)w.g.KH * w.g.KW * w.g.Cin;
+    if (w.gemm_ok) {
+      w.off_whi = off; off = align_up(off + (size_t)w.cout_pad * K * sizeof(__half));
+      w.off_wlo = off; off = align_up(off + (size_t)w.cout_pad * K * sizeof(__half));
+    }
+    w.off_wref = off;  off = align_up(off + K * w.g.Cout * sizeof(float));
+    w.off_alpha = off; off = align_up(off + (size_t)w.cout_pad * sizeof(float));
+    w.off_beta = off;  off = align_up(off + (size_t)w.cout_pad * sizeof(float));
+  }
+  off_ones_ = off; off = align_up(off + 4096 * sizeof(float));
+  if (cfg_.with_mask) {
+    off_deconv_w_ = off; off = align_up(off + (size_t)256 * 7200 * sizeof(float));
+    off_deconv_b_ = off; off = align_up(off + 32 * sizeof(float));
+  }
+  blob_bytes_ = off;
+}
+
+Engine::Engine(const sm_config& cfg) : cfg_(cfg), exact_(cfg.precision == SM_PRECISION_EXACT) {
+  SMK_CHECK(cfg.search_size >= 127 && (cfg.search_size - 127) % 8 == 0, "search_size must be 127 + 8k");
+  SMK_CHECK(cfg.max_batch >= 1 && cfg.num_slots >= cfg.max_batch, "need num_slots >= max_batch >= 1");
+  SMK_CHECK(cfg.anchor_num >= 1, "anchor_num");
+  int dev = 0;
+  SMK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  SMK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  SMK_CHECK(prop.major == 10, "siammask_b200 kernels are built for sm_100a only (found sm_" +
+                                  std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+  num_sms_ = prop.multiProcessorCount;
+  R_ = (cfg.search_size - 127) / 8 + 1 + 8;   // utils/tracker_config.py:23,46 with base_size 8
+
+  build_layer_table();
+  assign_blob_layout();
+  SMK_CUDA(cudaMalloc(&blob_, blob_bytes_));
+  for (auto& kv : layers_) {
+    ConvW& w = kv.second;
+    if (w.gemm_ok) {
+      w.w_hi = reinterpret_cast<__half*>(blob_ + w.off_whi);
+      w.w_lo = reinterpret_cast<__half*>(blob_ + w.off_wlo);
+    }
+    w.w_ref = reinterpret_cast<float*>(blob_ + w.off_wref);
+    w.alpha = reinterpret_cast<float*>(blob_ + w.off_alpha);
+    w.beta = reinterpret_cast<float*>(blob_ + w.off_beta);
+  }
+  ones_ = reinterpret_cast<float*>(blob_ + off_ones_);
+  if (cfg_.with_mask) {
+    deconv_w_ = reinterpret_cast<float*>(blob_ + off_deconv_w_);
+    deconv_b_ = reinterpret_cast<float*>(blob_ + off_deconv_b_);
+  }
+
+  // workspace sizes: dry-run the schedule with a measuring arena
+  search_arena_.cap = measure_arena(cfg.max_batch, cfg.search_size, true);
+  templ_arena_.cap = measure_arena(cfg.max_batch, 127, false);
+  SMK_CUDA(cudaMalloc(&search_arena_.base, search_arena_.cap));
+  SMK_CUDA(cudaMalloc(&templ_arena_.base, templ_arena_.cap));
+  if (cfg_.with_mask) {
+    // refine stage: crops + conv outputs, ~ (61*61*64 + 31*31*(256+64) + 15*15*(512+128)) split + fp32 maps
+    refine_arena_.cap = align_up((size_t)cfg.max_batch * 6u * 1024 * 1024 + (1u << 20));
+    SMK_CUDA(cudaMalloc(&refine_arena_.base, refine_arena_.cap));
+  }
+  const size_t kc = (size_t)n_branches_ * cfg.num_slots * 25 * 256;
+  SMK_CUDA(cudaMalloc(&kcache_hi_, kc * sizeof(__half)));
+  SMK_CUDA(cudaMalloc(&kcache_lo_, kc * sizeof(__half)));
+  SMK_CUDA(cudaMemset(kcache_hi_, 0, kc * sizeof(__half)));
+  SMK_CUDA(cudaMemset(kcache_lo_, 0, kc * sizeof(__half)));
+
+  const size_t B = cfg.max_batch, S = cfg.search_size, A = cfg.anchor_num;
+  SMK_CUDA(cudaMalloc(&stage_x_, B * 3 * S * S * sizeof(float)));
+  SMK_CUDA(cudaMalloc(&stage_cls_, B * 2 * A * R_ * R_ * sizeof(float)));
+  SMK_CUDA(cudaMalloc(&stage_loc_, B * 4 * A * R_ * R_ * sizeof(float)));
+  SMK_CUDA(cudaMalloc(&stage_mask_, B * 127 * 127 * sizeof(float)));
+  SMK_CUDA(cudaMalloc(&stage_pos_, B * 2 * sizeof(int32_t)));
+
+  // nearest-upsample index tables (custom.py:150-152) + identity tables
+  const int pairs[6][2] = {{31, 15}, {61, 31}, {127, 61}, {15, 15}, {31, 31}, {61, 61}};
+  std::vector<int> all;
+  std::vector<size_t> offs;
+  for (auto& pr : pairs) {
+    offs.push_back(all.size());
+    auto t = nearest_index_table(pr[0], pr[1]);
+    all.insert(all.end(), t.begin(), t.end());
+  }
+  SMK_CUDA(cudaMalloc(&maps_dev_, all.size() * sizeof(int)));
+  SMK_CUDA(cudaMemcpy(maps_dev_, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice));
+  for (int i = 0; i < 6; ++i) maps_[pairs[i][0] * 1000 + pairs[i][1]] = maps_dev_ + offs[i];
+
+  total_bytes_ = blob_bytes_ + search_arena_.cap + templ_arena_.cap + refine_arena_.cap + 2 * kc * sizeof(__half) +
+                 (B * 3 * S * S + B * 6 * A * R_ * R_ + B * 127 * 127) * sizeof(float);
+}
+
+Engine::~Engine() {
+  cudaFree(blob_);
+  cudaFree(search_arena_.base);
+  cudaFree(templ_arena_.base);
+  cudaFree(refine_arena_.base);
+  cudaFree(kcache_hi_);
+  cudaFree(kcache_lo_);
+  cudaFree(stage_x_);
+  cudaFree(stage_cls_);
+  cudaFree(stage_loc_);
+  cudaFree(stage_mask_);
+  cudaFree(stage_pos_);
+  cudaFree(maps_dev_);
+}
+
+size_t Engine::measure_arena(int B, int S, bool search) {
+  Arena ar;
+  ar.measure = true;
+  measuring_ = true;
+  Act xf = backbone(nullptr, B, S, ar, search, nullptr);
+  if (search) {
+    // heads: conv_search, corr, head.0 per branch
+    for (int br = 0; br < n_branches_; ++br) {
+      alloc_act(ar, B, xf.H - 2, xf.W - 2, 256);
+      alloc_act(ar, B, R_, R_, 256);
+      alloc_act(ar, B, R_, R_, 256);
+    }
+  }
+  measuring_ = false;
+  named_.clear();
+  return align_up(ar.peak + (1u << 20));
+}
+
+// ================================================================================================
+// weight ingest
+
+namespace {
+const float* find_tensor(const std::map<std::string, const sm_tensor_desc*>& sd, const std::string& name,
+                         size_t expect_numel) {
+  auto it = sd.find(name);
+  SMK_CHECK(it != sd.end(), "checkpoint is missing tensor '" + name + "'");
+  size_t n = 1;
+  for (int i = 0; i < it->second->ndim; ++i) n *= (size_t)it->second->shape[i];
+  SMK_CHECK(n == expect_numel, "tensor '" + name + "' has " + std::to_string(n) + " elements, expected " +
+                                   std::to_string(expect_numel));
+  return it->second->data;
+}
+}  // namespace
+
+void Engine::pack_layer(ConvW& L, const std::map<std::string, const sm_tensor_desc*>& sd, uint8_t* host) {
+  const ConvGeom& g = L.g;
+  const size_t K = (size_t)g.KH * g.KW * g.Cin;
+  const float* w = find_tensor(sd, L.conv_key + ".weight", K * g.Cout);   // OIHW
+  std::vector<double> scale(g.Cout, 1.0), shift(g.Cout, 0.0);
+  if (!L.bn_key.empty()) {
+    const float* gm = find_tensor(sd, L.bn_key + ".weight", g.Cout);
+    const float* bt = find_tensor(sd, L.bn_key + ".bias", g.Cout);
+    const float* mu = find_tensor(sd, L.bn_key + ".running_mean", g.Cout);
+    const float* var = find_tensor(sd, L.bn_key + ".running_var", g.Cout);
+    for (int n = 0; n < g.Cout; ++n) {
+      scale[n] = (double)gm[n] / std::sqrt((double)var[n] + (double)BN_EPS);
+      shift[n] = (double)bt[n] - (double)mu[n] * scale[n];
+    }
+  } else {
+    const float* b = find_tensor(sd, L.conv_key + ".bias", g.Cout);
+    for (int n = 0; n < g.Cout; ++n) shift[n] = b[n];
+  }
+  float* w_ref = reinterpret_cast<float*>(host + L.off_wref);
+  float* alpha = reinterpret_cast<float*>(host + L.off_alpha);
+  float* beta = reinterpret_cast<float*>(host + L.off_beta);
+  __half* w_hi = L.gemm_ok ? reinterpret_cast<__half*>(host + L.off_whi) : nullptr;
+  __half* w_lo = L.gemm_ok ? reinterpret_cast<__half*>(host + L.off_wlo) : nullptr;
+  for (int n = 0; n < L.cout_pad; ++n) { alpha[n] = 0.f; beta[n] = 0.f; }
+  const int HW = g.KH * g.KW;
+  for (int n = 0; n < g.Cout; ++n) {
+    // folded weight row (fp32), and its largest magnitude
+    float amax = 0.f;
+    for (int c = 0; c < g.Cin; ++c)
+      for (int t = 0; t < HW; ++t) {
+        const float fw = (float)((double)w[((size_t)n * g.Cin + c) * HW + t] * scale[n]);
+        w_ref[((size_t)t * g.Cin + c) * g.Cout + n] = fw;
+        amax = std::max(amax, std::fabs(fw));
+      }
+    beta[n] = (float)shift[n];
+    alpha[n] = 1.f;
+    if (L.gemm_ok) {
+      // per-output-channel power-of-two scaling keeps hi AND lo fp16 parts in the normal range;
+      // the epilogue multiplies the accumulator back by 2^-e (exact).
+      int e = 0;
+      if (amax > 0.f) e = (int)std::floor(std::log2(16384.0 / (double)amax));
+      e = std::max(-24, std::min(24, e));
+      const float up = std::ldexp(1.f, e);
+      alpha[n] = std::ldexp(1.f, -e);
+      for (int c = 0; c < g.Cin; ++c)
+        for (int t = 0; t < HW; ++t) {
+          const float fw = w_ref[((size_t)t * g.Cin + c) * g.Cout + n] * up;
+          const __half h = __float2half_rn(fw);
+          const size_t idx = ((size_t)n * HW + t) * g.Cin + c;
+          w_hi[idx] = h;
+          w_lo[idx] = __float2half_rn(fw - __half2float(h));
+        }
+    }
+  }
+  if (L.gemm_ok)
+    for (size_t i = (size_t)g.Cout * K; i < (size_t)L.cout_pad * K; ++i) { w_hi[i] = __float2half_rn(0.f); w_lo[i] = w_hi[i]; }
+}
+
+void Engine::load_weights(const sm_tensor_desc* t, int n) {
+  std::map<std::string, const sm_tensor_desc*> sd;
+  for (int i = 0; i < n; ++i) {
+    SMK_CHECK(t[i].name != nullptr && t[i].data != nullptr, "null tensor descriptor");
+    std::string name = t[i].name;
+    if (name.rfind("module.", 0) == 0) name = name.substr(7);   // utils/load_helper.py:22-27
+    sd[name] = &t[i];
+  }
+  std::vector<uint8_t> host(blob_bytes_, 0);
+  for (const auto& k : layer_order_) pack_layer(layers_[k], sd, host.data());
+  float* ones = reinterpret_cast<float*>(host.data() + off_ones_);
+  for (int i = 0; i < 4096; ++i) ones[i] = 1.f;
+  if (cfg_.with_mask) {
+    // ConvTranspose2d weight (Cin=256, Cout=32, 15, 15) -> [k][(y*15+x)*32 + co]
+    const float* dw = find_tensor(sd, "refine_model.deconv.weight", (size_t)256 * 32 * 225);
+    const float* db = find_tensor(sd, "refine_model.deconv.bias", 32);
+    float* wd = reinterpret_cast<float*>(host.data() + off_deconv_w_);
+    for (int k = 0; k < 256; ++k)
+      for (int co = 0; co < 32; ++co)
+        for (int p = 0; p < 225; ++p) wd[(size_t)k * 7200 + p * 32 + co] = dw[((size_t)k * 32 + co) * 225 + p];
+    std::memcpy(host.data() + off_deconv_b_, db, 32 * sizeof(float));
+  }
+  SMK_CUDA(cudaMemcpy(blob_, host.data(), blob_bytes_, cudaMemcpyHostToDevice));
+  weights_ready_ = true;
+}
+
+// ================================================================================================
+// schedule helpers
+
+Act Engine::alloc_act(Arena& ar, int B, int H, int W, int C) {
+  Act a;
+  a.B = B; a.H = H; a.W = W; a.C = C;
+  a.hi = static_cast<__half*>(ar.alloc(a.numel() * sizeof(__half)));
+  a.lo = exact_ ? static_cast<__half*>(ar.alloc(a.numel() * sizeof(__half))) : nullptr;
+  return a;
+}
+
+F32T Engine::alloc_f32(Arena& ar, int B, int H, int W, int C) {
+  F32T t;
+  t.B = B; t.H = H; t.W = W; t.C = C;
+  t.p = static_cast<float*>(ar.alloc((size_t)B * H * W * C * sizeof(float)));
+  return t;
+}
+
+void Engine::conv_into(const Act& in, const ConvW& Lw, Epilogue ep, cudaStream_t st) {
+  if (measuring_) return;
+  ep.beta = Lw.beta;
+  ++launches_;
+  if (cfg_.backend == SM_BACKEND_TENSOR && Lw.gemm_ok) {
+    ep.alpha = Lw.alpha;
+    launch_gemm_conv(in, Lw.g, Lw.w_hi, Lw.w_lo, Lw.cout_pad, ep, exact_ ? 2 : 1, num_sms_, st);
+  } else {
+    ep.alpha = ones_;
+    launch_ref_conv(in, Lw.g, Lw.w_ref, ep, st);
+  }
+}
+
+Act Engine::conv(const Act& in, const ConvW& Lw, bool relu, const Act* res, Arena& ar, cudaStream_t st) {
+  Act out = alloc_act(ar, in.B, Lw.g.out_size(in.H), Lw.g.out_size(in.W), Lw.g.Cout);
+  Epilogue ep;
+  ep.relu = relu ? 1 : 0;
+  ep.out_mode = OUT_NHWC_SPLIT;
+  ep.out_hi = out.hi;
+  ep.out_lo = out.lo;
+  if (res != nullptr) { ep.res_hi = res->hi; ep.res_lo = res->lo; }
+  conv_into(in, Lw, ep, st);
+  return out;
+}
+
+F32T Engine::conv_f32(const Act& in, const ConvW& Lw, bool relu, Arena& ar, cudaStream_t st) {
+  F32T out = alloc_f32(ar, in.B, Lw.g.out_size(in.H), Lw.g.out_size(in.W), Lw.g.Cout);
+  Epilogue ep;
+  ep.relu = relu ? 1 : 0;
+  ep.out_mode = OUT_NHWC_F32;
+  ep.out_f32 = out.p;
+  conv_into(in, Lw, ep, st);
+  return out;
+}
+
+// ResDown.forward / forward_all (custom.py:58-66): ResNet (resnet.py:217-227) + ResDownS (custom.py:19-25)
+Act Engine::backbone(const float* x, int B, int S, Arena& ar, bool keep, cudaStream_t st) {
+  const std::string F = "features.features.";
+  const int So = (S - 7) / 2 + 1;
+  Act p0 = alloc_act(ar, B, So, So, 64);
+  const ConvW& stem = L(F + "conv1");
+  if (!measuring_) { launch_stem(x, B, S, stem.w_ref, ones_, stem.beta, p0, st); ++launches_; }
+  const int Sp = (So + 2 - 3) / 2 + 1;
+  Act y = alloc_act(ar, B, Sp, Sp, 64);
+  if (!measuring_) { launch_maxpool3s2(p0, y, st); ++launches_; }
+  if (keep) named_["p0"] = p0;
+  const char* names[3] = {"layer1", "layer2", "layer3"};
+  const int blocks[3] = {3, 4, 6};
+  for (int l = 0; l < 3; ++l) {
+    for (int i = 0; i < blocks[l]; ++i) {
+      const std::string P = F + names[l] + "." + std::to_string(i) + ".";
+      Act t1 = conv(y, L(P + "conv1"), true, nullptr, ar, st);
+      Act t2 = conv(t1, L(P + "conv2"), true, nullptr, ar, st);
+      Act res = y;
+      if (i == 0) res = conv(y, L(P + "downsample.0"), false, nullptr, ar, st);
+      y = conv(t2, L(P + "conv3"), true, &res, ar, st);
+    }
+    if (keep) named_[std::string("p") + std::to_string(l + 1)] = y;
+  }
+  Act xf = conv(y, L("features.downsample.downsample.0"), false, nullptr, ar, st);
+  if (xf.W < 20) {   // custom.py:21-24
+    Act c = alloc_act(ar, B, xf.H - 8, xf.W - 8, xf.C);
+    if (!measuring_) { launch_crop_center(xf, 4, c, st); ++launches_; }
+    xf = c;
+  }
+  return xf;
+}
+
+static const char* kBranch[3] = {"rpn_model.cls.", "rpn_model.loc.", "mask_model.mask."};
+static const char* kCorrName[3] = {"corr_cls", "corr_loc", "corr_mask"};
+
+void Engine::do_template(int slot0, int B, const float* z, cudaStream_t st) {
+  SMK_CHECK(weights_ready_, "weights not loaded");
+  SMK_CHECK(B >= 1 && B <= cfg_.max_batch && slot0 >= 0 && slot0 + B <= cfg_.num_slots, "template batch/slot range");
+  templ_arena_.reset();
+  Act zf = backbone(z, B, 127, templ_arena_, false, st);
+  SMK_CHECK(zf.H == 7 && zf.W == 7, "template feature must be 7x7");
+  named_["zf"] = zf;
+  for (int br = 0; br < n_branches_; ++br) {
+    const ConvW& ck = L(std::string(kBranch[br]) + "conv_kernel.0");
+    Epilogue ep;
+    ep.relu = 1;
+    ep.out_mode = OUT_NHWC_SPLIT;
+    const size_t off = ((size_t)br * cfg_.num_slots + slot0) * 25 * 256;
+    ep.out_hi = kcache_hi_ + off;
+    ep.out_lo = exact_ ? kcache_lo_ + off : nullptr;
+    conv_into(zf, ck, ep, st);
+  }
+}
+
+void Engine::do_track(int slot0, int B, const float* x, float* cls, float* loc, float* mask, int flags,
+                      cudaStream_t st) {
+  SMK_CHECK(weights_ready_, "weights not loaded");
+  SMK_CHECK(B >= 1 && B <= cfg_.max_batch && slot0 >= 0 && slot0 + B <= cfg_.num_slots, "track batch/slot range");
+  SMK_CHECK(cls != nullptr && loc != nullptr, "cls/loc outputs required");
+  const bool want_feats = (flags & SM_TRACK_MASK_FEATURES) != 0;
+  const bool want_mask_head = (flags & SM_TRACK_MASK_HEAD) != 0;
+  SMK_CHECK(!(want_feats || want_mask_head) || cfg_.with_mask, "engine was built without the mask branch");
+  SMK_CHECK(!want_mask_head || mask != nullptr, "mask output buffer required");
+  search_arena_.reset();
+  Act zf_keep;
+  bool had_zf = named_.count("zf") > 0;
+  if (had_zf) zf_keep = named_["zf"];
+  named_.clear();
+  if (had_zf) named_["zf"] = zf_keep;
+  Act xf = backbone(x, B, cfg_.search_size, search_arena_, true, st);
+  named_["search"] = xf;
+  const int nb = (want_feats || want_mask_head) ? 3 : 2;
+  float* outs[3] = {cls, loc, mask};
+  for (int br = 0; br < nb; ++br) {
+    const std::string P = kBranch[br];
+    Act cs = conv(xf, L(P + "conv_search.0"), true, nullptr, search_arena_, st);
+    Act corr = alloc_act(search_arena_, B, cs.H - 4, cs.W - 4, 256);
+    const size_t off = ((size_t)br * cfg_.num_slots + slot0) * 25 * 256;
+    launch_xcorr_nhwc(cs, kcache_hi_ + off, exact_ ? kcache_lo_ + off : nullptr, 5, 5, corr, st);
+    ++launches_;
+    named_[kCorrName[br]] = corr;
+    if (br == 2 && !want_mask_head) break;
+    Act h = conv(corr, L(P + "head.0"), true, nullptr, search_arena_, st);
+    Epilogue ep;
+    ep.relu = 0;
+    ep.out_mode = OUT_NCHW_F32;
+    ep.out_f32 = outs[br];
+    conv_into(h, L(P + "head.3"), ep, st);
+  }
+  last_B_ = B;
+  have_mask_feats_ = want_feats || want_mask_head;
+}
+
+F32T Engine::small(const F32T& a, const F32T* b, int Ho, const ConvW& Lw, bool relu, float* out_override, Arena& ar,
+                   cudaStream_t st) {
+  F32T out;
+  out.B = a.B; out.H = Ho; out.W = Ho; out.C = Lw.g.Cout;
+  out.p = out_override != nullptr ? out_override
+                                  : static_cast<float*>(ar.alloc((size_t)a.B * Ho * Ho * Lw.g.Cout * sizeof(float)));
+  SMK_CHECK(a.C == Lw.g.Cin && (b == nullptr || (b->C == a.C && b->H == a.H)), "small conv operand shapes");
+  const int* map = updown_map(Ho, a.H);
+  launch_small_conv3x3_maps(a.p, b ? b->p : nullptr, a.B, a.H, a.W, Ho, Ho, a.C, Lw.g.Cout, map, map, Lw.w_ref, Lw.beta,
+                            relu ? 1 : 0, out.p, st);
+  ++launches_;
+  return out;
+}
+
+// Refine.forward(test=True), custom.py:131-154, one (dy,dx) per stream
+void Engine::do_refine(int B, const int32_t* pos, float* out, cudaStream_t st) {
+  SMK_CHECK(cfg_.with_mask, "engine was built without the mask branch");
+  SMK_CHECK(have_mask_feats_ && B == last_B_, "sm_refine must follow sm_track(..., SM_TRACK_MASK_FEATURES) with the same B");
+  Arena& ar = refine_arena_;
+  ar.reset();
+  const std::string R = "refine_model.";
+  const Act& p0 = named_["p0"];
+  const Act& p1 = named_["p1"];
+  const Act& p2 = named_["p2"];
+  const Act& corr = named_["corr_mask"];
+  // p3 = corr_feature[:, :, dy, dx]; out = deconv(p3)
+  float* p3 = static_cast<float*>(ar.alloc((size_t)B * 256 * sizeof(float)));
+  launch_gather_corr(corr, pos, p3, st); ++launches_;
+  F32T d = alloc_f32(ar, B, 15, 15, 32);
+  launch_deconv(p3, deconv_w_, deconv_b_, d.p, B, 256, 7200, 32, st); ++launches_;
+  // level 2 (15x15): post0(up31(h2(out) + v2(p2)))
+  Act c2 = alloc_act(ar, B, 15, 15, 512);
+  launch_refine_crop(p2, pos, 1, 4, 15, c2, st); ++launches_;
+  Act v2a = conv(c2, L(R + "v2.0"), true, nullptr, ar, st);
+  F32T v2b = conv_f32(v2a, L(R + "v2.2"), true, ar, st);
+  F32T h2a = small(d, nullptr, 15, L(R + "h2.0"), true, nullptr, ar, st);
+  F32T h2b = small(h2a, nullptr, 15, L(R + "h2.2"), true, nullptr, ar, st);
+  F32T o0 = small(h2b, &v2b, 31, L(R + "post0"), false, nullptr, ar, st);
+  // level 1 (31x31)
+  Act c1 = alloc_act(ar, B, 31, 31, 256);
+  launch_refine_crop(p1, pos, 2, 8, 31, c1, st); ++launches_;
+  Act v1a = conv(c1, L(R + "v1.0"), true, nullptr, ar, st);
+  F32T v1b = conv_f32(v1a, L(R + "v1.2"), true, ar, st);
+  F32T h1a = small(o0, nullptr, 31, L(R + "h1.0"), true, nullptr, ar, st);
+  F32T h1b = small(h1a, nullptr, 31, L(R + "h1.2"), true, nullptr, ar, st);
+  F32T o1 = small(h1b, &v1b, 61, L(R + "post1"), false, nullptr, ar, st);
+  // level 0 (61x61)
+  Act c0 = alloc_act(ar, B, 61, 61, 64);
+  launch_refine_crop(p0, pos, 4, 16, 61, c0, st); ++launches_;
+  F32T v0a = conv_f32(c0, L(R + "v0.0"), true, ar, st);
+  F32T v0b = small(v0a, nullptr, 61, L(R + "v0.2"), true, nullptr, ar, st);
+  F32T h0a = small(o1, nullptr, 61, L(R + "h0.0"), true, nullptr, ar, st);
+  F32T h0b = small(h0a, nullptr, 61, L(R + "h0.2"), true, nullptr, ar, st);
+  small(h0b, &v0b, 127, L(R + "post2"), false, out, ar, st);   // (B,127,127,1) == (B,127*127)
+}
+
+void Engine::track_host(int slot0, int B, const float* xh, float* clsh, float* loch, const int32_t* posh, float* maskh,
+                        cudaStream_t st) {
+  const size_t S = cfg_.search_size, A = cfg_.anchor_num;
+  const size_t nx = (size_t)B * 3 * S * S, ncls = (size_t)B * 2 * A * R_ * R_, nloc = 2 * ncls;
+  SMK_CUDA(cudaMemcpyAsync(stage_x_, xh, nx * sizeof(float), cudaMemcpyHostToDevice, st));
+  const bool refine = posh != nullptr && maskh != nullptr;
+  do_track(slot0, B, stage_x_, stage_cls_, stage_loc_, nullptr, refine ? SM_TRACK_MASK_FEATURES : 0, st);
+  SMK_CUDA(cudaMemcpyAsync(clsh, stage_cls_, ncls * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SMK_CUDA(cudaMemcpyAsync(loch, stage_loc_, nloc * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (refine) {
+    SMK_CUDA(cudaMemcpyAsync(stage_pos_, posh, (size_t)B * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    do_refine(B, stage_pos_, stage_mask_, st);
+    SMK_CUDA(cudaMemcpyAsync(maskh, stage_mask_, (size_t)B * 127 * 127 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  SMK_CUDA(cudaStreamSynchronize(st));
+}
+
+void Engine::do_export(const char* what, float* out, int64_t* shape4, cudaStream_t st) {
+  auto it = named_.find(what);
+  SMK_CHECK(it != named_.end(), std::string("no cached tensor named '") + what + "'");
+  const Act& a = it->second;
+  if (shape4 != nullptr) { shape4[0] = a.B; shape4[1] = a.C; shape4[2] = a.H; shape4[3] = a.W; }
+  if (out != nullptr) { launch_split_to_f32(a, out, st); ++launches_; }
+}
+
+// ================================================================================================
+// standalone conv operator (kernel-level parity tests)
+
+static void conv2d_op(const float* x, const float* w, const float* scale, const float* shift, float* out, int B,
+                      int Cin, int H, int W, int Cout, int KH, int KW, int stride, int pad, int dil, int relu,
+                      int backend, int precision, cudaStream_t st) {
+  ConvGeom g{Cin, Cout, KH, KW, stride, pad, dil};
+  const bool exact = precision == SM_PRECISION_EXACT;
+  const bool use_gemm = backend == SM_BACKEND_TENSOR;
+  SMK_CHECK(!use_gemm || gemm_conv_supported(g), "tensor-core conv needs Cin % 64 == 0");
+  const size_t K = (size_t)KH * KW * Cin;
+  const int cout_pad = use_gemm ? gemm_cout_pad(Cout) : Cout;
+  std::vector<float> hw(K * Cout), hs(Cout, 1.f), hb(Cout, 0.f);
+  SMK_CUDA(cudaStreamSynchronize(st));
+  SMK_CUDA(cudaMemcpy(hw.data(), w, hw.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  if (scale) SMK_CUDA(cudaMemcpy(hs.data(), scale, Cout * sizeof(float), cudaMemcpyDeviceToHost));
+  if (shift) SMK_CUDA(cudaMemcpy(hb.data(), shift, Cout * sizeof(float), cudaMemcpyDeviceToHost));
+  std::vector<float> wref(K * Cout), alpha(cout_pad, 0.f), beta(cout_pad, 0.f);
+  std::vector<__half> whi((size_t)cout_pad * K, __float2half_rn(0.f)), wlo((size_t)cout_pad * K, __float2half_rn(0.f));
+  const int HW = KH * KW;
+  for (int n = 0; n < Cout; ++n) {
+    float amax = 0.f;
+    for (int c = 0; c < Cin; ++c)
+      for (int t = 0; t < HW; ++t) {
+        const float fw = (float)((double)hw[((size_t)n * Cin + c) * HW + t] * (double)hs[n]);
+        wref[((size_t)t * Cin + c) * Cout + n] = fw;
+        amax = std::max(amax, std::fabs(fw));
+      }
+    beta[n] = hb[n];
+    alpha[n] = 1.f;
+    if (use_gemm) {
+      int e = amax > 0.f ? (int)std::floor(std::log2(16384.0 / (double)amax)) : 0;
+      e = std::max(-24, std::min(24, e));
+      alpha[n] = std::ldexp(1.f, -e);
+      for (int c = 0; c < Cin; ++c)
+        for (int t = 0; t < HW; ++t) {
+          const float fw = std::ldexp(wref[((size_t)t * Cin + c) * Cout + n], e);
+          const __half h = __float2half_rn(fw);
+          whi[((size_t)n * HW + t) * Cin + c] = h;
+          wlo[((size_t)n * HW + t) * Cin + c] = __float2half_rn(fw - __half2float(h));
+        }
+    }
+  }
+  const int Ho = g.out_size(H), Wo = g.out_size(W);
+  Act in;
+  in.B = B; in.H = H; in.W = W; in.C = Cin;
+  __half *d_whi = nullptr, *d_wlo = nullptr;
+  float *d_wref = nullptr, *d_alpha = nullptr, *d_beta = nullptr;
+  SMK_CUDA(cudaMalloc(&in.hi, in.numel() * sizeof(__half)));
+  if (exact) SMK_CUDA(cudaMalloc(&in.lo, in.numel() * sizeof(__half)));
+  SMK_CUDA(cudaMalloc(&d_whi, whi.size() * sizeof(__half)));
+  SMK_CUDA(cudaMalloc(&d_wlo, wlo.size() * sizeof(__half)));
+  SMK_CUDA(cudaMalloc(&d_wref, wref.size() * sizeof(float)));
+  SMK_CUDA(cudaMalloc(&d_alpha, alpha.size() * sizeof(float)));
+  SMK_CUDA(cudaMalloc(&d_beta, beta.size() * sizeof(float)));
+  SMK_CUDA(cudaMemcpy(d_whi, whi.data(), whi.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  SMK_CUDA(cudaMemcpy(d_wlo, wlo.data(), wlo.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  SMK_CUDA(cudaMemcpy(d_wref, wref.data(), wref.size() * sizeof(float), cudaMemcpyHostToDevice));
+  SMK_CUDA(cudaMemcpy(d_alpha, alpha.data(), alpha.size() * sizeof(float), cudaMemcpyHostToDevice));
+  SMK_CUDA(cudaMemcpy(d_beta, beta.data(), beta.size() * sizeof(float), cudaMemcpyHostToDevice));
+  launch_import_nchw(x, in, st);
+  Epilogue ep;
+  ep.alpha = d_alpha;
+  ep.beta = d_beta;
+  ep.relu = relu;
+  ep.out_mode = OUT_NCHW_F32;
+  ep.out_f32 = out;
+  int dev = 0, sms = 148;
+  SMK_CUDA(cudaGetDevice(&dev));
+  SMK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  (void)Ho; (void)Wo;
+  if (use_gemm) launch_gemm_conv(in, g, d_whi, d_wlo, cout_pad, ep, exact ? 2 : 1, sms, st);
+  else launch_ref_conv(in, g, d_wref, ep, st);
+  SMK_CUDA(cudaStreamSynchronize(st));
+  cudaFree(in.hi); cudaFree(in.lo); cudaFree(d_whi); cudaFree(d_wlo); cudaFree(d_wref); cudaFree(d_alpha); cudaFree(d_beta);
+}
+
+}  // namespace smk
+
+// ================================================================================================
+// C ABI
+
+struct sm_engine {
+  std::unique_ptr<smk::Engine> impl;
+};
+
+#define SM_API_BEGIN try {
+#define SM_API_END                                  \
+  return 0;                                         \
+  }                                                 \
+  catch (const std::exception& ex) {                \
+    smk::g_last_error = ex.what();                  \
+    return -1;                                      \
+  }                                                 \
+  catch (...) {                                     \
+    smk::g_last_error = "unknown error";            \
+    return -1;                                      \
+  }
+
+extern "C" {
+
+const char* sm_last_error(void) { return smk::g_last_error.c_str(); }
+const char* sm_version(void) { return "siammask_b200 0.1 (sm_100a)"; }
+
+int sm_engine_create(const sm_config* cfg, sm_engine** out) {
+  SM_API_BEGIN
+  SMK_CHECK(cfg != nullptr && out != nullptr, "null argument");
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  SMK_CHECK(err == cudaSuccess && ndev > 0, "no CUDA device: siammask_b200 has no CPU fallback");
+  auto* e = new sm_engine;
+  try {
+    e->impl.reset(new smk::Engine(*cfg));
+  } catch (...) {
+    delete e;
+    throw;
+  }
+  *out = e;
+  SM_API_END
+}
+
+void sm_engine_destroy(sm_engine* e) { delete e; }
+
+int sm_engine_load_weights(sm_engine* e, const sm_tensor_desc* tensors, int32_t n) {
+  SM_API_BEGIN
+  SMK_CHECK(e && tensors && n > 0, "null argument");
+  e->impl->load_weights(tensors, n);
+  SM_API_END
+}
+
+int sm_engine_weight_blob(sm_engine* e, void** dev_ptr, size_t* bytes) {
+  SM_API_BEGIN
+  SMK_CHECK(e && dev_ptr && bytes, "null argument");
+  e->impl->weight_blob(dev_ptr, bytes);
+  SM_API_END
+}
+
+int sm_engine_adopt_weights(sm_engine* e) {
+  SM_API_BEGIN
+  SMK_CHECK(e, "null argument");
+  e->impl->adopt_weights();
+  SM_API_END
+}
+
+int sm_template(sm_engine* e, int32_t slot0, int32_t B, const float* z, void* stream) {
+  SM_API_BEGIN
+  SMK_CHECK(e && z, "null argument");
+  e->impl->do_template(slot0, B, z, static_cast<cudaStream_t>(stream));
+  SM_API_END
+}
+
+int sm_track(sm_engine* e, int32_t slot0, int32_t B, const float* x, float* cls, float* loc, float* mask, int32_t flags,
+             void* stream) {
+  SM_API_BEGIN
+  SMK_CHECK(e && x, "null argument");
+  e->impl->do_track(slot0, B, x, cls, loc, mask, flags, static_cast<cudaStream_t>(stream));
+  SM_API_END
+}
+
+int sm_refine(sm_engine* e, int32_t B, const int32_t* pos, float* out, void* stream) {
+  SM_API_BEGIN
+  SMK_CHECK(e && pos && out, "null argument");
+  e->impl->do_refine(B, pos, out, static_cast<cudaStream_t>(stream));
+  SM_API_END
+}
+
+int sm_track_host(sm_engine* e, int32_t slot0, int32_t B, const float* x_host, float* cls_host, float* loc_host,
+                  const int32_t* pos_host, float* mask_out_host, void* stream) {
+  SM_API_BEGIN
+  SMK_CHECK(e && x_host && cls_host && loc_host, "null argument");
+  e->impl->track_host(slot0, B, x_host, cls_host, loc_host, pos_host, mask_out_host, static_cast<cudaStream_t>(stream));
+  SM_API_END
+}
+
+int sm_xcorr_depthwise(const float* x, const float* k, float* out, int32_t B, int32_t C, int32_t H, int32_t W, int32_t kh,
+                       int32_t kw, void* stream) {
+  SM_API_BEGIN
+  SMK_CHECK(x && k && out, "null argument");
+  int ndev = 0;
+  SMK_CHECK(cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0, "no CUDA device: siammask_b200 has no CPU fallback");
+  smk::launch_xcorr_nchw_f32(x, k, out, B * C, H, W, kh, kw, static_cast<cudaStream_t>(stream));
+  SM_API_END
+}
+
+int sm_conv2d(const float* x, const float* w, const float* scale, const float* shift, float* out, int32_t B, int32_t Cin,
+              int32_t H, int32_t W, int32_t Cout, int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t dil,
+              int32_t relu, int32_t backend, int32_t precision, void* stream) {
+  SM_API_BEGIN
+  SMK_CHECK(x && w && out, "null argument");
+  int ndev = 0;
+  SMK_CHECK(cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0, "no CUDA device: siammask_b200 has no CPU fallback");
+  smk::conv2d_op(x, w, scale, shift, out, B, Cin, H, W, Cout, KH, KW, stride, pad, dil, relu, backend, precision,
+                 static_cast<cudaStream_t>(stream));
+  SM_API_END
+}
+
+int sm_export(sm_engine* e, const char* what, float* out, int64_t* shape4, void* stream) {
+  SM_API_BEGIN
+  SMK_CHECK(e && what, "null argument");
+  e->impl->do_export(what, out, shape4, static_cast<cudaStream_t>(stream));
+  SM_API_END
+}
+
+int64_t sm_launch_count(const sm_engine* e) { return e ? e->impl->launches() : 0; }
+size_t sm_engine_bytes(const sm_engine* e) { return e ? e->impl->bytes() : 0; }
+
+}  // extern "C"

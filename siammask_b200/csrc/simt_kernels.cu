@@ -1,0 +1,535 @@
+// CUDA-core kernels of the SiamMask hot path (sm_100a): everything that is not a dense contraction
+// large enough for the tensor pipe — the 3-channel 7x7 stem, max-pool, the bandwidth-bound depthwise
+// cross-correlation, the crops/gathers of the refine stage, its 1-32 channel 3x3 convs and the
+// 1x1 -> 15x15 transposed conv — plus a plain reference convolution used to bisect the tcgen05 path.
+#include "common.cuh"
+
+#include <cmath>
+#include <vector>
+
+namespace smk {
+
+namespace {
+
+__device__ __forceinline__ float split_load(const __half* hi, const __half* lo, size_t i) {
+  float v = __half2float(hi[i]);
+  if (lo != nullptr) v += __half2float(lo[i]);
+  return v;
+}
+__device__ __forceinline__ void split_store(__half* hi, __half* lo, size_t i, float v) {
+  const __half h = __float2half_rn(v);
+  hi[i] = h;
+  if (lo != nullptr) lo[i] = __float2half_rn(v - __half2float(h));
+}
+__device__ __forceinline__ float2 split_load2(const __half* hi, const __half* lo, size_t i) {
+  float2 v = __half22float2(*reinterpret_cast<const __half2*>(hi + i));
+  if (lo != nullptr) {
+    const float2 l = __half22float2(*reinterpret_cast<const __half2*>(lo + i));
+    v.x += l.x;
+    v.y += l.y;
+  }
+  return v;
+}
+__device__ __forceinline__ void split_store2(__half* hi, __half* lo, size_t i, float2 v) {
+  const __half2 h = __floats2half2_rn(v.x, v.y);
+  *reinterpret_cast<__half2*>(hi + i) = h;
+  if (lo != nullptr) {
+    const float2 hf = __half22float2(h);
+    *reinterpret_cast<__half2*>(lo + i) = __floats2half2_rn(v.x - hf.x, v.y - hf.y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reference convolution (one thread per output element, fp32 accumulate).  Same epilogue contract
+// as the tensor-core kernel.  Weights: fp32 [KH][KW][Cin][Cout].
+__global__ void ref_conv_kernel(Act in, ConvGeom g, const float* __restrict__ w, Epilogue ep, int Ho, int Wo) {
+  const size_t total = (size_t)in.B * Ho * Wo * g.Cout;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int n = idx % g.Cout;
+    const size_t m = idx / g.Cout;
+    const int wo = m % Wo;
+    const int ho = (m / Wo) % Ho;
+    const int b = m / ((size_t)Wo * Ho);
+    float acc = 0.f;
+    for (int r = 0; r < g.KH; ++r) {
+      const int hi_ = ho * g.stride - g.pad + r * g.dil;
+      if (hi_ < 0 || hi_ >= in.H) continue;
+      for (int s = 0; s < g.KW; ++s) {
+        const int wi = wo * g.stride - g.pad + s * g.dil;
+        if (wi < 0 || wi >= in.W) continue;
+        const size_t ibase = (((size_t)b * in.H + hi_) * in.W + wi) * in.C;
+        const float* wp = w + ((size_t)(r * g.KW + s) * g.Cin) * g.Cout + n;
+        for (int c = 0; c < g.Cin; ++c) acc = fmaf(split_load(in.hi, in.lo, ibase + c), wp[(size_t)c * g.Cout], acc);
+      }
+    }
+    float v = fmaf(acc, ep.alpha[n], ep.beta[n]);
+    if (ep.res_hi != nullptr) v += split_load(ep.res_hi, ep.res_lo, m * g.Cout + n);
+    if (ep.relu) v = fmaxf(v, 0.f);
+    if (ep.out_mode == OUT_NHWC_SPLIT) split_store(ep.out_hi, ep.out_lo, m * g.Cout + n, v);
+    else if (ep.out_mode == OUT_NHWC_F32) ep.out_f32[m * g.Cout + n] = v;
+    else ep.out_f32[((size_t)b * g.Cout + n) * Ho * Wo + (size_t)ho * Wo + wo] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem: 7x7 stride-2 pad-0 conv, 3 -> 64 channels, + BN + ReLU (resnet.py:154,218-220).
+// Input: raw NCHW fp32 pixels (the boundary layout, tools/test.py:61-64); output: p0, NHWC split planes.
+// Block = 16x8 output pixels x 64 channels; thread = 2 horizontally adjacent pixels x 16 channels.
+constexpr int ST_TW = 16, ST_TH = 8, ST_PW = ST_TW * 2 + 5, ST_PH = ST_TH * 2 + 5;
+
+__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, int S, int So,
+                                                   const float* __restrict__ w,      // [7][7][3][64]
+                                                   const float* __restrict__ alpha, const float* __restrict__ beta,
+                                                   Act out) {
+  __shared__ __align__(16) float sw[147 * 64];
+  __shared__ float sp[3][ST_PH][ST_PW];
+  const int b = blockIdx.z;
+  const int oy0 = blockIdx.y * ST_TH, ox0 = blockIdx.x * ST_TW;
+  for (int i = threadIdx.x; i < 147 * 64; i += 256) sw[i] = w[i];
+  const float* xb = x + (size_t)b * 3 * S * S;
+  for (int i = threadIdx.x; i < 3 * ST_PH * ST_PW; i += 256) {
+    const int c = i / (ST_PH * ST_PW);
+    const int rem = i - c * (ST_PH * ST_PW);
+    const int py = rem / ST_PW, px = rem - py * ST_PW;
+    const int iy = oy0 * 2 + py, ix = ox0 * 2 + px;
+    sp[c][py][px] = (iy < S && ix < S) ? xb[((size_t)c * S + iy) * S + ix] : 0.f;
+  }
+  __syncthreads();
+  const int cg = threadIdx.x >> 6;          // channel group of 16 (warp-uniform)
+  const int pp = threadIdx.x & 63;          // pixel pair
+  const int ty = pp >> 3, tx = (pp & 7) * 2;
+  float acc0[16], acc1[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+  for (int r = 0; r < 7; ++r) {
+    for (int s = 0; s < 7; ++s) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float a0 = sp[c][ty * 2 + r][tx * 2 + s];
+        const float a1 = sp[c][ty * 2 + r][tx * 2 + 2 + s];
+        const float4* wv = reinterpret_cast<const float4*>(&sw[((r * 7 + s) * 3 + c) * 64 + cg * 16]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 q = wv[j];
+          acc0[4 * j + 0] = fmaf(a0, q.x, acc0[4 * j + 0]); acc1[4 * j + 0] = fmaf(a1, q.x, acc1[4 * j + 0]);
+          acc0[4 * j + 1] = fmaf(a0, q.y, acc0[4 * j + 1]); acc1[4 * j + 1] = fmaf(a1, q.y, acc1[4 * j + 1]);
+          acc0[4 * j + 2] = fmaf(a0, q.z, acc0[4 * j + 2]); acc1[4 * j + 2] = fmaf(a1, q.z, acc1[4 * j + 2]);
+          acc0[4 * j + 3] = fmaf(a0, q.w, acc0[4 * j + 3]); acc1[4 * j + 3] = fmaf(a1, q.w, acc1[4 * j + 3]);
+        }
+      }
+    }
+  }
+  const int oy = oy0 + ty;
+#pragma unroll
+  for (int px = 0; px < 2; ++px) {
+    const int ox = ox0 + tx + px;
+    if (oy >= So || ox >= So) continue;
+    const float* acc = px == 0 ? acc0 : acc1;
+    const size_t base = (((size_t)b * So + oy) * So + ox) * 64 + cg * 16;
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      float2 v;
+      v.x = fmaxf(fmaf(acc[j], alpha[cg * 16 + j], beta[cg * 16 + j]), 0.f);
+      v.y = fmaxf(fmaf(acc[j + 1], alpha[cg * 16 + j + 1], beta[cg * 16 + j + 1]), 0.f);
+      split_store2(out.hi, out.lo, base + j, v);
+    }
+  }
+}
+
+// 3x3 stride-2 pad-1 max-pool over NHWC split planes (resnet.py:158,221); thread = pixel x channel pair.
+__global__ void maxpool_kernel(Act in, Act out) {
+  const size_t total = out.numel() / 2;
+  const int c2n = out.C / 2;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (idx % c2n) * 2;
+    const size_t m = idx / c2n;
+    const int wo = m % out.W, ho = (m / out.W) % out.H;
+    const int b = m / ((size_t)out.W * out.H);
+    float2 best = make_float2(-INFINITY, -INFINITY);
+    for (int r = 0; r < 3; ++r) {
+      const int hi_ = ho * 2 - 1 + r;
+      if (hi_ < 0 || hi_ >= in.H) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int wi = wo * 2 - 1 + s;
+        if (wi < 0 || wi >= in.W) continue;
+        const float2 v = split_load2(in.hi, in.lo, (((size_t)b * in.H + hi_) * in.W + wi) * in.C + c);
+        best.x = fmaxf(best.x, v.x);
+        best.y = fmaxf(best.y, v.y);
+      }
+    }
+    split_store2(out.hi, out.lo, m * out.C + c, best);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depthwise cross-correlation, NHWC split planes (engine-internal form of conv2d_dw_group,
+// models/rpn.py:32-38): out[b,i,j,c] = sum_{u,v} x[b,i+u,j+v,c] * k[b,u,v,c].
+// Thread = (b, output row i, channel pair); it slides a KHxKW register window along j so every
+// input element is fetched KH times (rows) instead of KH*KW times; lanes are consecutive channel
+// pairs, so each warp load/store is one contiguous 128-byte line.
+template <int KH, int KW>
+__global__ void __launch_bounds__(128) xcorr_nhwc_kernel(Act x, const __half* __restrict__ k_hi,
+                                                         const __half* __restrict__ k_lo, Act out) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (c >= x.C) return;
+  const int i = blockIdx.y, b = blockIdx.z;
+  float2 kk[KH][KW];
+#pragma unroll
+  for (int u = 0; u < KH; ++u)
+#pragma unroll
+    for (int v = 0; v < KW; ++v) kk[u][v] = split_load2(k_hi, k_lo, (((size_t)b * KH + u) * KW + v) * x.C + c);
+  float2 win[KH][KW];
+#pragma unroll
+  for (int u = 0; u < KH; ++u)
+#pragma unroll
+    for (int v = 0; v < KW - 1; ++v)
+      win[u][v + 1] = split_load2(x.hi, x.lo, (((size_t)b * x.H + i + u) * x.W + v) * x.C + c);
+  for (int j = 0; j < out.W; ++j) {
+#pragma unroll
+    for (int u = 0; u < KH; ++u) {
+#pragma unroll
+      for (int v = 0; v < KW - 1; ++v) win[u][v] = win[u][v + 1];
+      win[u][KW - 1] = split_load2(x.hi, x.lo, (((size_t)b * x.H + i + u) * x.W + j + KW - 1) * x.C + c);
+    }
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < KH; ++u)
+#pragma unroll
+      for (int v = 0; v < KW; ++v) {
+        acc.x = fmaf(win[u][v].x, kk[u][v].x, acc.x);
+        acc.y = fmaf(win[u][v].y, kk[u][v].y, acc.y);
+      }
+    split_store2(out.hi, out.lo, (((size_t)b * out.H + i) * out.W + j) * out.C + c, acc);
+  }
+}
+
+// Standalone operator with the reference's own layout (fp32 NCHW, models/rpn.py:32-38): one warp per
+// (b,c) plane.  Lane l owns input column j0+l; the KW-wide window is assembled with warp shuffles, so
+// every input element is read from memory exactly once per column pass; KH partial output rows are
+// carried in registers and retired as soon as their last input row has been consumed.
+template <int KH, int KW>
+__global__ void __launch_bounds__(256) xcorr_nchw_kernel(const float* __restrict__ x, const float* __restrict__ k,
+                                                         float* __restrict__ out, int planes, int H, int W) {
+  const int plane = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (plane >= planes) return;
+  const int lane = threadIdx.x & 31;
+  const int Ho = H - KH + 1, Wo = W - KW + 1;
+  const float* xp = x + (size_t)plane * H * W;
+  const float* kp = k + (size_t)plane * KH * KW;
+  float* op = out + (size_t)plane * Ho * Wo;
+  float kk[KH][KW];
+#pragma unroll
+  for (int u = 0; u < KH; ++u)
+#pragma unroll
+    for (int v = 0; v < KW; ++v) kk[u][v] = __ldg(kp + u * KW + v);
+  constexpr int COLS = 32 - KW + 1;   // output columns produced per pass
+  for (int j0 = 0; j0 < Wo; j0 += COLS) {
+    const int col = j0 + lane;
+    const bool in_ok = col < W;
+    const bool out_ok = lane < COLS && col < Wo;
+    float acc[KH];
+#pragma unroll
+    for (int u = 0; u < KH; ++u) acc[u] = 0.f;
+    constexpr int RB = 8;               // rows fetched per batch (memory-level parallelism)
+    for (int r0 = 0; r0 < H; r0 += RB) {
+      float rowv[RB];
+#pragma unroll
+      for (int t = 0; t < RB; ++t) rowv[t] = (in_ok && r0 + t < H) ? __ldg(xp + (size_t)(r0 + t) * W + col) : 0.f;
+#pragma unroll
+      for (int t = 0; t < RB; ++t) {
+        const int r = r0 + t;
+        if (r < H) {   // warp-uniform
+          float xv[KW];
+          xv[0] = rowv[t];
+#pragma unroll
+          for (int v = 1; v < KW; ++v) xv[v] = __shfl_down_sync(0xffffffffu, rowv[t], v);
+          // acc[u] holds output row r-u
+#pragma unroll
+          for (int u = 0; u < KH; ++u)
+#pragma unroll
+            for (int v = 0; v < KW; ++v) acc[u] = fmaf(xv[v], kk[u][v], acc[u]);
+          const int done = r - (KH - 1);
+          if (done >= 0 && done < Ho && out_ok) op[(size_t)done * Wo + col] = acc[KH - 1];
+#pragma unroll
+          for (int u = KH - 1; u > 0; --u) acc[u] = acc[u - 1];
+          acc[0] = 0.f;
+        }
+      }
+    }
+  }
+}
+
+// Generic fallback for other kernel sizes (thread per output element).
+__global__ void xcorr_nchw_generic_kernel(const float* __restrict__ x, const float* __restrict__ k,
+                                          float* __restrict__ out, int planes, int H, int W, int kh, int kw) {
+  const int Ho = H - kh + 1, Wo = W - kw + 1;
+  const size_t total = (size_t)planes * Ho * Wo;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int j = idx % Wo, i = (idx / Wo) % Ho;
+    const size_t pl = idx / ((size_t)Wo * Ho);
+    float acc = 0.f;
+    for (int u = 0; u < kh; ++u)
+      for (int v = 0; v < kw; ++v) acc = fmaf(x[(pl * H + i + u) * W + j + v], k[(pl * kh + u) * kw + v], acc);
+    out[idx] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ResDownS crop x[:, :, 4:-4, 4:-4] (custom.py:21-24) and the refine-stage windows
+// pad(f, P)[scale*dy : scale*dy+size, scale*dx : ...] (custom.py:133-135), zero outside the feature map.
+__global__ void crop_kernel(Act in, Act out, const int32_t* __restrict__ pos, int scale, int padv, int fixed_off) {
+  const size_t total = out.numel() / 8;   // 8 halfs (16 B) per thread
+  const int c8n = out.C / 8;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (idx % c8n) * 8;
+    const size_t m = idx / c8n;
+    const int xo = m % out.W, yo = (m / out.W) % out.H;
+    const int b = m / ((size_t)out.W * out.H);
+    int yi, xi;
+    if (pos != nullptr) {
+      yi = scale * pos[2 * b] + yo - padv;
+      xi = scale * pos[2 * b + 1] + xo - padv;
+    } else {
+      yi = yo + fixed_off;
+      xi = xo + fixed_off;
+    }
+    uint4 h = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
+    if (yi >= 0 && yi < in.H && xi >= 0 && xi < in.W) {
+      const size_t src = (((size_t)b * in.H + yi) * in.W + xi) * in.C + c;
+      h = *reinterpret_cast<const uint4*>(in.hi + src);
+      if (in.lo != nullptr) l = *reinterpret_cast<const uint4*>(in.lo + src);
+    }
+    const size_t dst = m * out.C + c;
+    *reinterpret_cast<uint4*>(out.hi + dst) = h;
+    if (out.lo != nullptr) *reinterpret_cast<uint4*>(out.lo + dst) = l;
+  }
+}
+
+// p3 = corr_feature[b, :, dy, dx] (custom.py:144-145) as fp32 [B][C]
+__global__ void gather_corr_kernel(Act corr, const int32_t* __restrict__ pos, float* __restrict__ out) {
+  const int b = blockIdx.x;
+  const int dy = pos[2 * b], dx = pos[2 * b + 1];
+  for (int c = threadIdx.x; c < corr.C; c += blockDim.x)
+    out[(size_t)b * corr.C + c] = split_load(corr.hi, corr.lo, (((size_t)b * corr.H + dy) * corr.W + dx) * corr.C + c);
+}
+
+// ConvTranspose2d(256, 32, 15, 15) on a 1x1 input (custom.py:120,149) == [B x Cin] x [Cin x N] + bias,
+// N = 15*15*32 ordered (y, x, co) so the result is NHWC fp32.  Thread = output column n, 8 samples.
+constexpr int DC_BT = 8;
+__global__ void __launch_bounds__(256) deconv_kernel(const float* __restrict__ p3, const float* __restrict__ w,
+                                                     const float* __restrict__ bias, float* __restrict__ out,
+                                                     int B, int Cin, int N, int cout) {
+  extern __shared__ float sp3[];   // [DC_BT][Cin]
+  const int b0 = blockIdx.y * DC_BT;
+  for (int i = threadIdx.x; i < DC_BT * Cin; i += blockDim.x) {
+    const int bb = b0 + i / Cin;
+    sp3[i] = bb < B ? p3[(size_t)bb * Cin + i % Cin] : 0.f;
+  }
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float acc[DC_BT];
+#pragma unroll
+  for (int t = 0; t < DC_BT; ++t) acc[t] = 0.f;
+  for (int k = 0; k < Cin; ++k) {
+    const float wv = __ldg(w + (size_t)k * N + n);
+#pragma unroll
+    for (int t = 0; t < DC_BT; ++t) acc[t] = fmaf(sp3[t * Cin + k], wv, acc[t]);
+  }
+  const float bv = bias[n % cout];
+#pragma unroll
+  for (int t = 0; t < DC_BT; ++t)
+    if (b0 + t < B) out[(size_t)(b0 + t) * N + n] = acc[t] + bv;
+}
+
+// NCHW fp32 -> NHWC split planes (standalone-operator entry, sm_conv2d).
+__global__ void import_nchw_kernel(const float* __restrict__ x, Act out) {
+  const size_t total = out.numel();
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = idx % out.C;
+    const int w = (idx / out.C) % out.W;
+    const int h = (idx / ((size_t)out.C * out.W)) % out.H;
+    const int b = idx / ((size_t)out.C * out.W * out.H);
+    split_store(out.hi, out.lo, idx, x[(((size_t)b * out.C + c) * out.H + h) * out.W + w]);
+  }
+}
+
+// NHWC split planes -> NCHW fp32 (exports cached features for parity checks / the Python boundary).
+__global__ void export_nchw_kernel(Act in, float* __restrict__ out) {
+  const size_t total = in.numel();
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int w = idx % in.W;
+    const int h = (idx / in.W) % in.H;
+    const int c = (idx / ((size_t)in.W * in.H)) % in.C;
+    const int b = idx / ((size_t)in.W * in.H * in.C);
+    out[idx] = split_load(in.hi, in.lo, (((size_t)b * in.H + h) * in.W + w) * in.C + c);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Refine-stage 3x3 pad-1 convs with 1..32 output channels on fp32 NHWC (custom.py:102-124,150-152).
+// The input is up(a (+ b)): an optional second operand (the h_i + v_i sum) and a nearest-neighbour
+// upsample (index tables computed on the host exactly as ATen does) are fused into the fetch.
+// Thread = one output pixel, all COUT channels in registers; weights [3][3][Cin][COUT] in smem.
+template <int COUT>
+__global__ void __launch_bounds__(128) small_conv3x3_kernel(const float* __restrict__ a, const float* __restrict__ b2,
+                                                            int B, int Hi, int Wi, int Ho, int Wo, int Cin,
+                                                            const int* __restrict__ ymap, const int* __restrict__ xmap,
+                                                            const float* __restrict__ w, const float* __restrict__ bias,
+                                                            int relu, float* __restrict__ out) {
+  extern __shared__ float sw[];   // 9*Cin*COUT weights
+  for (int i = threadIdx.x; i < 9 * Cin * COUT; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const size_t m = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (m >= (size_t)B * Ho * Wo) return;
+  const int xo = m % Wo, yo = (m / Wo) % Ho;
+  const int b = m / ((size_t)Wo * Ho);
+  float acc[COUT];
+#pragma unroll
+  for (int j = 0; j < COUT; ++j) acc[j] = bias[j];
+  for (int r = 0; r < 3; ++r) {
+    const int y = yo + r - 1;
+    if (y < 0 || y >= Ho) continue;
+    const int ys = ymap[y];
+    for (int s = 0; s < 3; ++s) {
+      const int x = xo + s - 1;
+      if (x < 0 || x >= Wo) continue;
+      const size_t src = (((size_t)b * Hi + ys) * Wi + xmap[x]) * Cin;
+      const float* wt = sw + (r * 3 + s) * Cin * COUT;
+      for (int c = 0; c < Cin; c += 4) {
+        float4 v = *reinterpret_cast<const float4*>(a + src + c);
+        if (b2 != nullptr) {
+          const float4 v2 = *reinterpret_cast<const float4*>(b2 + src + c);
+          v.x += v2.x; v.y += v2.y; v.z += v2.z; v.w += v2.w;
+        }
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) {
+          acc[j] = fmaf(v.x, wt[(c + 0) * COUT + j], acc[j]);
+          acc[j] = fmaf(v.y, wt[(c + 1) * COUT + j], acc[j]);
+          acc[j] = fmaf(v.z, wt[(c + 2) * COUT + j], acc[j]);
+          acc[j] = fmaf(v.w, wt[(c + 3) * COUT + j], acc[j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < COUT; ++j) out[m * COUT + j] = relu ? fmaxf(acc[j], 0.f) : acc[j];
+}
+
+inline int grid_for(size_t total, int block) {
+  size_t g = (total + block - 1) / block;
+  return (int)(g > 148 * 64 ? 148 * 64 : (g == 0 ? 1 : g));
+}
+
+}  // namespace
+
+// ================================================================================================
+void launch_ref_conv(const Act& in, const ConvGeom& g, const float* w, const Epilogue& ep, cudaStream_t st) {
+  const int Ho = g.out_size(in.H), Wo = g.out_size(in.W);
+  const size_t total = (size_t)in.B * Ho * Wo * g.Cout;
+  ref_conv_kernel<<<grid_for(total, 256), 256, 0, st>>>(in, g, w, ep, Ho, Wo);
+  SMK_CUDA(cudaGetLastError());
+}
+
+void launch_stem(const float* x, int B, int S, const float* w, const float* alpha, const float* beta, Act out,
+                 cudaStream_t st) {
+  const int So = (S - 7) / 2 + 1;
+  SMK_CHECK(out.H == So && out.W == So && out.C == 64 && out.B == B, "stem output shape");
+  dim3 grid((So + ST_TW - 1) / ST_TW, (So + ST_TH - 1) / ST_TH, B);
+  stem_kernel<<<grid, 256, 0, st>>>(x, S, So, w, alpha, beta, out);
+  SMK_CUDA(cudaGetLastError());
+}
+
+void launch_maxpool3s2(const Act& in, Act out, cudaStream_t st) {
+  SMK_CHECK(out.H == (in.H + 2 - 3) / 2 + 1 && out.C == in.C && out.B == in.B, "maxpool output shape");
+  maxpool_kernel<<<grid_for(out.numel() / 2, 256), 256, 0, st>>>(in, out);
+  SMK_CUDA(cudaGetLastError());
+}
+
+void launch_xcorr_nhwc(const Act& x, const __half* k_hi, const __half* k_lo, int kh, int kw, Act out, cudaStream_t st) {
+  SMK_CHECK(kh == 5 && kw == 5, "engine xcorr is specialised for the 5x5 template kernel");
+  SMK_CHECK(out.H == x.H - kh + 1 && out.W == x.W - kw + 1 && out.C == x.C && x.C % 2 == 0, "xcorr shapes");
+  dim3 grid((x.C / 2 + 127) / 128, out.H, x.B);
+  xcorr_nhwc_kernel<5, 5><<<grid, 128, 0, st>>>(x, k_hi, k_lo, out);
+  SMK_CUDA(cudaGetLastError());
+}
+
+void launch_xcorr_nchw_f32(const float* x, const float* k, float* out, int planes, int H, int W, int kh, int kw,
+                           cudaStream_t st) {
+  SMK_CHECK(H >= kh && W >= kw && planes > 0, "xcorr shapes");
+  if (kh == 5 && kw == 5) {
+    const int warps = 8;
+    xcorr_nchw_kernel<5, 5><<<(planes + warps - 1) / warps, warps * 32, 0, st>>>(x, k, out, planes, H, W);
+  } else {
+    const size_t total = (size_t)planes * (H - kh + 1) * (W - kw + 1);
+    xcorr_nchw_generic_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, k, out, planes, H, W, kh, kw);
+  }
+  SMK_CUDA(cudaGetLastError());
+}
+
+void launch_crop_center(const Act& in, int crop, Act out, cudaStream_t st) {
+  SMK_CHECK(out.H == in.H - 2 * crop && out.C == in.C && in.C % 8 == 0, "crop shapes");
+  crop_kernel<<<grid_for(out.numel() / 8, 256), 256, 0, st>>>(in, out, nullptr, 0, 0, crop);
+  SMK_CUDA(cudaGetLastError());
+}
+
+void launch_refine_crop(const Act& in, const int32_t* pos, int scale, int padv, int size, Act out, cudaStream_t st) {
+  SMK_CHECK(out.H == size && out.W == size && out.C == in.C && in.C % 8 == 0, "refine crop shapes");
+  crop_kernel<<<grid_for(out.numel() / 8, 256), 256, 0, st>>>(in, out, pos, scale, padv, 0);
+  SMK_CUDA(cudaGetLastError());
+}
+
+void launch_gather_corr(const Act& corr, const int32_t* pos, float* out, cudaStream_t st) {
+  gather_corr_kernel<<<corr.B, 256, 0, st>>>(corr, pos, out);
+  SMK_CUDA(cudaGetLastError());
+}
+
+void launch_deconv(const float* p3, const float* w, const float* bias, float* out, int B, int Cin, int N, int cout,
+                   cudaStream_t st) {
+  dim3 grid((N + 255) / 256, (B + DC_BT - 1) / DC_BT);
+  deconv_kernel<<<grid, 256, DC_BT * Cin * sizeof(float), st>>>(p3, w, bias, out, B, Cin, N, cout);
+  SMK_CUDA(cudaGetLastError());
+}
+
+void launch_split_to_f32(const Act& in, float* out, cudaStream_t st) {
+  export_nchw_kernel<<<grid_for(in.numel(), 256), 256, 0, st>>>(in, out);
+  SMK_CUDA(cudaGetLastError());
+}
+
+void launch_import_nchw(const float* x, Act out, cudaStream_t st) {
+  import_nchw_kernel<<<grid_for(out.numel(), 256), 256, 0, st>>>(x, out);
+  SMK_CUDA(cudaGetLastError());
+}
+
+// Host-side nearest-neighbour source index, computed the way ATen does for F.upsample(mode='nearest')
+// (custom.py:150-152): src = min(floorf(dst * (float)in / out), in - 1).
+std::vector<int> nearest_index_table(int out_size, int in_size) {
+  std::vector<int> t(out_size);
+  const float scale = (float)in_size / (float)out_size;
+  for (int d = 0; d < out_size; ++d) {
+    int s = (int)floorf((float)d * scale);
+    t[d] = s < in_size - 1 ? s : in_size - 1;
+  }
+  return t;
+}
+
+void launch_small_conv3x3_maps(const float* a, const float* b, int B, int Hi, int Wi, int Ho, int Wo, int Cin, int Cout,
+                               const int* ymap, const int* xmap, const float* w, const float* bias, int relu,
+                               float* out, cudaStream_t st) {
+  SMK_CHECK(Cin % 4 == 0, "small conv needs Cin % 4 == 0");
+  const size_t M = (size_t)B * Ho * Wo;
+  const int grid = (int)((M + 127) / 128);
+  const size_t smem = (size_t)9 * Cin * Cout * sizeof(float);
+#define SMK_SC(CO)                                                                                               \
+  case CO:                                                                                                       \
+    small_conv3x3_kernel<CO><<<grid, 128, smem, st>>>(a, b, B, Hi, Wi, Ho, Wo, Cin, ymap, xmap, w, bias, relu, out); \
+    break;
+  switch (Cout) {
+    SMK_SC(1) SMK_SC(4) SMK_SC(16) SMK_SC(32)
+    default: SMK_CHECK(false, "small conv: unsupported Cout");
+  }
+#undef SMK_SC
+  SMK_CUDA(cudaGetLastError());
+}
+
+}  // namespace smk

@@ -1,0 +1,225 @@
+"""Drop-in replacement for the reference's `Custom` model object (experiments/siammask_sharp/custom.py:162-190,
+experiments/siamrpn_resnet/custom.py:81-93) as used by the tracker loop in tools/test.py:
+
+    siamese_init  :155       net.template(z)
+    siamese_track :201,203   net.track_mask(x) / net.track(x)
+    siamese_track :257       net.track_refine((delta_y, delta_x))
+    siamese_init  :137,142-145   net.anchors, net.anchor_num
+    main          :560-569   Custom(anchors=cfg['anchors']); load_pretrain(model, path); model.eval().to(device)
+
+Python here is plumbing only: tensors in, tensors out, every FLOP happens in libsiammask_b200.so
+(hand-written sm_100a kernels) reached through the C ABI in include/siammask_b200.h.
+
+Batched extension (not in the reference): every method accepts B>1 *paired* templates/searches
+bound to engine slots slot0..slot0+B-1, and `track_refine` additionally accepts an int tensor/array [B,2]
+of per-stream positions (the reference applies one (dy,dx) to the whole batch, custom.py:131-135).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from .checkpoint import expected_keys, normalize_keys
+
+DEFAULT_ANCHORS = {"stride": 8, "ratios": [0.33, 0.5, 1, 2, 3], "scales": [8], "round_dight": 0}
+
+
+class Custom:
+    def __init__(self, pretrain: bool = False, anchors: dict | None = None, *, search_size: int = 255,
+                 max_batch: int = 1, num_slots: int | None = None, precision: str = "exact",
+                 backend: str = "tensor", mask: bool = True, **_unused):
+        self.anchors = anchors if anchors is not None else dict(DEFAULT_ANCHORS)      # siammask_sharp.py:16
+        self.anchor_num = len(self.anchors["ratios"]) * len(self.anchors["scales"])   # siammask_sharp.py:17
+        self.search_size = int(search_size)
+        self.max_batch = int(max_batch)
+        self.num_slots = int(num_slots) if num_slots is not None else self.max_batch
+        self.precision = {"exact": _lib.SM_PRECISION_EXACT, "fast": _lib.SM_PRECISION_FAST}[precision]
+        self.backend = {"tensor": _lib.SM_BACKEND_TENSOR, "simt": _lib.SM_BACKEND_SIMT}[backend]
+        self.with_mask = bool(mask)
+        self.score_size = (self.search_size - 127) // 8 + 1 + 8            # utils/tracker_config.py:23
+        self.training = False
+        self._sd: dict[str, torch.Tensor] | None = None
+        self._engine = C.c_void_p(None)
+        self._device: torch.device | None = None
+        self._lib = _lib.load()
+
+    # ------------------------------------------------------------------ nn.Module protocol subset
+    def state_dict(self):
+        if self._sd is not None:
+            return OrderedDict(self._sd)
+        return OrderedDict((k, torch.empty(s, device="meta")) for k, s in
+                           expected_keys(self.with_mask, self.with_mask).items())
+
+    def load_state_dict(self, state_dict, strict: bool = False):
+        sd = normalize_keys(state_dict)
+        want = expected_keys(self.with_mask, self.with_mask)
+        missing = [k for k in want if k not in sd]
+        if missing:
+            raise KeyError(f"checkpoint lacks {len(missing)} tensors needed on the hot path, e.g. {missing[:3]}")
+        for k, shp in want.items():
+            if tuple(sd[k].shape) != tuple(shp):
+                raise ValueError(f"{k}: shape {tuple(sd[k].shape)} != expected {tuple(shp)}")
+        self._sd = {k: sd[k].detach().to("cpu", torch.float32).contiguous() for k in want}
+        if self._engine.value:
+            self._upload()
+        return self
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("siammask_b200 implements the inference path only")
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", torch.cuda.current_device() if device is None else device))
+
+    def to(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("siammask_b200 runs on CUDA (sm_100a) devices only; there is no CPU path")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        if self._engine.value and self._device == device:
+            return self
+        self._destroy()
+        self._device = device
+        with torch.cuda.device(device):
+            cfg = _lib.SmConfig(self.search_size, self.max_batch, self.num_slots, self.precision, self.backend,
+                                self.anchor_num, int(self.with_mask))
+            _lib.check(self._lib.sm_engine_create(C.byref(cfg), C.byref(self._engine)))
+            if self._sd is not None:
+                self._upload()
+        return self
+
+    # ------------------------------------------------------------------ weights
+    def _upload(self):
+        descs = (_lib.SmTensorDesc * len(self._sd))()
+        keep = []
+        for i, (k, t) in enumerate(self._sd.items()):
+            name = k.encode()
+            keep.append(name)
+            descs[i].name = name
+            descs[i].data = t.data_ptr()
+            descs[i].ndim = t.dim()
+            for j, s in enumerate(t.shape):
+                descs[i].shape[j] = s
+        with torch.cuda.device(self._device):
+            _lib.check(self._lib.sm_engine_load_weights(self._engine, descs, len(self._sd)))
+
+    def weight_blob(self) -> torch.Tensor:
+        """uint8 CUDA view of the engine's packed weight arena (for the one-off NCCL broadcast)."""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        _lib.check(self._lib.sm_engine_weight_blob(self._engine, C.byref(ptr), C.byref(n)))
+
+        class _Arena:
+            __cuda_array_interface__ = {"shape": (n.value,), "typestr": "|u1", "data": (ptr.value, False),
+                                        "version": 2}
+        t = torch.as_tensor(_Arena(), device=self._device)
+        t._sm_owner = self           # keep the engine alive while the view exists
+        return t
+
+    def adopt_weights(self):
+        _lib.check(self._lib.sm_engine_adopt_weights(self._engine))
+
+    # ------------------------------------------------------------------ the tracker-facing API
+    def _prep(self, t: torch.Tensor, size: int) -> torch.Tensor:
+        if not self._engine.value:
+            raise RuntimeError("call .to(cuda device) (and load weights) before inference")
+        if t.dim() != 4 or t.shape[1] != 3 or t.shape[2] != size or t.shape[3] != size:
+            raise ValueError(f"expected [B,3,{size},{size}], got {tuple(t.shape)}")
+        if t.shape[0] > self.max_batch:
+            raise ValueError(f"batch {t.shape[0]} > max_batch {self.max_batch}")
+        return t.to(self._device, torch.float32).contiguous()
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
+
+    @torch.no_grad()
+    def template(self, z, slot0: int = 0):
+        z = self._prep(z, 127)
+        with torch.cuda.device(self._device):
+            _lib.check(self._lib.sm_template(self._engine, slot0, z.shape[0], z.data_ptr(), self._stream()))
+
+    def _track(self, x, slot0, flags):
+        x = self._prep(x, self.search_size)
+        B, A, R = x.shape[0], self.anchor_num, self.score_size
+        cls = torch.empty(B, 2 * A, R, R, device=self._device, dtype=torch.float32)
+        loc = torch.empty(B, 4 * A, R, R, device=self._device, dtype=torch.float32)
+        mask = None
+        if flags & _lib.SM_TRACK_MASK_HEAD:
+            mask = torch.empty(B, 63 * 63, R, R, device=self._device, dtype=torch.float32)
+        with torch.cuda.device(self._device):
+            _lib.check(self._lib.sm_track(self._engine, slot0, B, x.data_ptr(), cls.data_ptr(), loc.data_ptr(),
+                                          mask.data_ptr() if mask is not None else None, flags, self._stream()))
+        self._last_B = B
+        return cls, loc, mask
+
+    @torch.no_grad()
+    def track(self, x, slot0: int = 0):
+        cls, loc, _ = self._track(x, slot0, 0)
+        return cls, loc
+
+    @torch.no_grad()
+    def track_mask(self, x, slot0: int = 0, mask_head: bool = True):
+        """mask_head=False skips the 256->3969 head, which tools/test.py:256-258 discards under --refine."""
+        flags = _lib.SM_TRACK_MASK_FEATURES | (_lib.SM_TRACK_MASK_HEAD if mask_head else 0)
+        return self._track(x, slot0, flags)
+
+    @torch.no_grad()
+    def track_refine(self, pos):
+        B = self._last_B
+        if isinstance(pos, torch.Tensor):
+            p = pos.to(self._device, torch.int32).reshape(-1, 2)
+        else:
+            p = torch.as_tensor(np.asarray(pos, dtype=np.int64).reshape(-1, 2).astype(np.int32), device=self._device)
+        if p.shape[0] == 1 and B > 1:
+            p = p.expand(B, 2)
+        p = p.contiguous()
+        if p.shape[0] != B:
+            raise ValueError(f"pos has {p.shape[0]} rows, last track had batch {B}")
+        R = self.score_size
+        if bool(((p < 0) | (p >= R)).any()):
+            raise IndexError(f"refine position out of range [0,{R})")
+        out = torch.empty(B, 127 * 127, device=self._device, dtype=torch.float32)
+        with torch.cuda.device(self._device):
+            _lib.check(self._lib.sm_refine(self._engine, B, p.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ introspection used by tests / bench
+    def export(self, what: str) -> torch.Tensor:
+        shape = (C.c_int64 * 4)()
+        with torch.cuda.device(self._device):
+            _lib.check(self._lib.sm_export(self._engine, what.encode(), None, shape, self._stream()))
+            out = torch.empty(*[int(s) for s in shape], device=self._device, dtype=torch.float32)
+            _lib.check(self._lib.sm_export(self._engine, what.encode(), out.data_ptr(), shape, self._stream()))
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.sm_launch_count(self._engine))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self._lib.sm_engine_bytes(self._engine))
+
+    @property
+    def handle(self):
+        return self._engine
+
+    def _destroy(self):
+        if self._engine.value:
+            self._lib.sm_engine_destroy(self._engine)
+            self._engine = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass

@@ -1,0 +1,62 @@
+"""Standalone operators of the hot path, bound to the C ABI (CUDA tensors in, CUDA tensors out).
+
+`conv2d_dw_group` keeps the reference's name and argument order (models/rpn.py:32-38)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def conv2d_dw_group(x: torch.Tensor, kernel: torch.Tensor) -> torch.Tensor:
+    """Depthwise cross-correlation: x f32[B,C,H,W], kernel f32[B,C,kh,kw] -> f32[B,C,H-kh+1,W-kw+1].
+    Like the reference it requires paired batches (kernel.shape[:2] == x.shape[:2])."""
+    if not (x.is_cuda and kernel.is_cuda):
+        raise RuntimeError("siammask_b200 operators run on CUDA tensors only; there is no CPU path")
+    if x.shape[:2] != kernel.shape[:2]:
+        raise RuntimeError(f"paired batch required: x {tuple(x.shape)} vs kernel {tuple(kernel.shape)}")
+    lib = _lib.load()
+    x = x.to(torch.float32).contiguous()
+    kernel = kernel.to(torch.float32).contiguous()
+    B, Cn, H, W = x.shape
+    kh, kw = kernel.shape[2:]
+    out = torch.empty(B, Cn, H - kh + 1, W - kw + 1, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sm_xcorr_depthwise(x.data_ptr(), kernel.data_ptr(), out.data_ptr(), B, Cn, H, W, kh, kw,
+                                          _stream(x.device)))
+    return out
+
+
+xcorr_depthwise = conv2d_dw_group
+
+
+def conv2d(x, weight, scale=None, shift=None, stride=1, padding=0, dilation=1, relu=False, backend="tensor",
+           precision="exact"):
+    """F.conv2d(x, weight) * scale[c] + shift[c] (+ReLU) through the engine's convolution kernels.
+    x f32[B,Cin,H,W] NCHW, weight f32[Cout,Cin,KH,KW]; returns f32 NCHW."""
+    if not x.is_cuda:
+        raise RuntimeError("siammask_b200 operators run on CUDA tensors only; there is no CPU path")
+    lib = _lib.load()
+    dev = x.device
+    x = x.to(torch.float32).contiguous()
+    weight = weight.to(dev, torch.float32).contiguous()
+    B, Cin, H, W = x.shape
+    Cout, _, KH, KW = weight.shape
+    Ho = (H + 2 * padding - dilation * (KH - 1) - 1) // stride + 1
+    Wo = (W + 2 * padding - dilation * (KW - 1) - 1) // stride + 1
+    out = torch.empty(B, Cout, Ho, Wo, device=dev, dtype=torch.float32)
+    sc = scale.to(dev, torch.float32).contiguous() if scale is not None else None
+    sh = shift.to(dev, torch.float32).contiguous() if shift is not None else None
+    be = {"tensor": _lib.SM_BACKEND_TENSOR, "simt": _lib.SM_BACKEND_SIMT}[backend]
+    pr = {"exact": _lib.SM_PRECISION_EXACT, "fast": _lib.SM_PRECISION_FAST}[precision]
+    with torch.cuda.device(dev):
+        _lib.check(lib.sm_conv2d(x.data_ptr(), weight.data_ptr(), sc.data_ptr() if sc is not None else None,
+                                 sh.data_ptr() if sh is not None else None, out.data_ptr(), B, Cin, H, W, Cout, KH, KW,
+                                 stride, padding, dilation, int(relu), be, pr, _stream(dev)))
+    return out
