@@ -103,6 +103,13 @@ int sm_conv2d(const float* x, const float* w, const float* scale, const float* s
  * with out == NULL only the shape is returned. */
 int sm_export(sm_engine* e, const char* what, float* out, int64_t* shape4, void* stream);
 
+/* Per-launch CUDA-event timing on the caller's stream (bench.py's roofline leg).  While enabled every kernel
+ * launch is bracketed by events; sm_profile_dump synchronises and returns tab-separated lines
+ * "name\tcategory\tms\tflops\tbytes\n" (algorithmic FLOPs / bytes of that launch) and clears the log.
+ * With buf == NULL or cap too small it returns the required size (call again). */
+int sm_profile_enable(sm_engine* e, int32_t on);
+int64_t sm_profile_dump(sm_engine* e, char* buf, size_t cap);
+
 /* Number of kernel launches the engine has issued since creation (bench.py reports it). */
 int64_t sm_launch_count(const sm_engine* e);
 /* Device bytes held by the engine (weights + workspace + caches). */

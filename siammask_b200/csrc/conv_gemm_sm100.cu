@@ -11,7 +11,8 @@
 //   in TMEM, double-buffered so the epilogue of tile i overlaps the main loop of tile i+1.
 // * Precision: NSPLIT=1 multiplies the fp16 hi planes only.  NSPLIT=2 ("exact") keeps activations and
 //   weights as hi+lo fp16 pairs (22 significant bits) and issues three MMAs per k-step
-//   (hi*hi + lo*hi + hi*lo) into the same fp32 accumulator — fp32-class results from the fp16 tensor pipe.
+//   (hi*hi into one TMEM accumulator, lo*hi + hi*lo into a second one, summed in the epilogue) — fp32-class
+//   results from the fp16 tensor pipe.
 // * Epilogue (4 warps, one TMEM lane quarter each): acc*alpha[c]+beta[c] (+residual) (ReLU) written as
 //   NHWC split-fp16 planes, NHWC fp32, or NCHW fp32 (the boundary layout of the reference's outputs,
 //   tools/test.py:205-206) — TMEM lanes are pixels, so NCHW stores are coalesced across the warp.
@@ -40,8 +41,13 @@ struct Cfg {
   static constexpr int STAGE_BYTES = NSPLIT * (A_TILE_BYTES + B_TILE_BYTES);
   static constexpr int RAW_STAGES = (SMEM_LIMIT - 2048) / STAGE_BYTES;
   static constexpr int STAGES = RAW_STAGES > 6 ? 6 : RAW_STAGES;
-  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
-                                   : (2 * BLOCK_N <= 256) ? 256 : 512;
+  // 2 pipeline stages x NSPLIT accumulators (exact mode keeps the hi*hi sum and the 2^-11-sized cross terms in
+  // separate TMEM accumulators: the tensor pipe truncates on every accumulate, so feeding small terms into the
+  // large running sum — or tripling the number of adds into it — costs accuracy; they are summed in the epilogue)
+  static constexpr int ACC_COLS = NSPLIT * BLOCK_N;
+  static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
+                                   : (2 * ACC_COLS <= 256) ? 256 : 512;
+  static_assert(2 * ACC_COLS <= 512, "TMEM capacity");
   static constexpr int CH = BLOCK_N < 32 ? 16 : 32;   // epilogue column chunk
   // one CTA per SM: keep the request above half of the SM's shared memory
   static constexpr int SMEM_BYTES_RAW = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -149,7 +155,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tcgen05_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      const uint32_t tmem_d = tmem_base + acc * C::ACC_COLS;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
@@ -164,8 +170,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
           if constexpr (NSPLIT == 2) {
             const uint64_t da_lo = umma_desc_kmajor_sw128(a_hi + A_TILE_BYTES + koff);
             const uint64_t db_lo = umma_desc_kmajor_sw128(b_hi + C::B_TILE_BYTES + koff);
-            umma_f16(tmem_d, da_lo, db_hi, idesc, 1u);
-            umma_f16(tmem_d, da_hi, db_lo, idesc, 1u);
+            umma_f16(tmem_d + BLOCK_N, da_lo, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16(tmem_d + BLOCK_N, da_hi, db_lo, idesc, 1u);
           }
         }
         umma_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
@@ -188,12 +194,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
       const bool row_ok = m < p.M;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * C::ACC_COLS;
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
         uint32_t r[CH];
         tmem_ld_chunk<CH>(taddr + c0, r);
-        tmem_ld_wait();
+        if constexpr (NSPLIT == 2) {
+          uint32_t r2[CH];
+          tmem_ld_chunk<CH>(taddr + BLOCK_N + c0, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < CH; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        } else {
+          tmem_ld_wait();
+        }
         const int n = n0 + c0;
         float v[CH];
 #pragma unroll
@@ -420,7 +434,10 @@ void launch_gemm_conv(const Act& in, const ConvGeom& g, const __half* w_hi, cons
     SMK_DISPATCH(32)
     SMK_DISPATCH(64)
     SMK_DISPATCH(128)
-    SMK_DISPATCH(256)
+    case 256:
+      SMK_CHECK(nsplit == 1, "exact mode uses N tiles <= 128 (two TMEM accumulators per tile)");
+      launch_cfg<256, 1>(p, num_sms, st);
+      break;
     default: SMK_CHECK(false, "unsupported N tile");
   }
 #undef SMK_DISPATCH

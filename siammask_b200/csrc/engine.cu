@@ -44,6 +44,12 @@ struct F32T {                         // fp32 NHWC tensor (refine stage)
   int B = 0, H = 0, W = 0, C = 0;
 };
 
+struct ProfRec {
+  std::string name, cat;
+  double flops = 0, bytes = 0;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
 struct Arena {
   uint8_t* base = nullptr;
   size_t cap = 0, off = 0, peak = 0;
@@ -77,6 +83,8 @@ class Engine {
                   cudaStream_t st);
   void do_export(const char* what, float* out, int64_t* shape4, cudaStream_t st);
 
+  void set_profiling(bool on) { profiling_ = on; }
+  std::string profile_dump();
   int64_t launches() const { return launches_; }
   size_t bytes() const { return total_bytes_; }
   const sm_config& cfg() const { return cfg_; }
@@ -145,6 +153,31 @@ class Engine {
   int64_t launches_ = 0;
   size_t total_bytes_ = 0;
   bool measuring_ = false;
+
+  // optional per-launch CUDA-event timing (bench.py roofline): records (name, category, flops, bytes, e0, e1)
+  bool profiling_ = false;
+  std::vector<ProfRec> prof_;
+  std::vector<cudaEvent_t> event_pool_;
+  cudaEvent_t get_event() {
+    if (!event_pool_.empty()) { cudaEvent_t e = event_pool_.back(); event_pool_.pop_back(); return e; }
+    cudaEvent_t e;
+    SMK_CUDA(cudaEventCreate(&e));
+    return e;
+  }
+  struct Scope {
+    Engine* eng; cudaStream_t st; size_t idx; bool on;
+    Scope(Engine* e, const std::string& name, const char* cat, double flops, double bytes, cudaStream_t s)
+        : eng(e), st(s), idx(0), on(e->profiling_ && !e->measuring_) {
+      if (!on) return;
+      ProfRec r;
+      r.name = name; r.cat = cat; r.flops = flops; r.bytes = bytes;
+      r.e0 = eng->get_event(); r.e1 = eng->get_event();
+      cudaEventRecord(r.e0, st);
+      idx = eng->prof_.size();
+      eng->prof_.push_back(r);
+    }
+    ~Scope() { if (on) cudaEventRecord(eng->prof_[idx].e1, st); }
+  };
 };
 
 // ================================================================================================
@@ -459,7 +492,12 @@ void Engine::conv_into(const Act& in, const ConvW& Lw, Epilogue ep, cudaStream_t
   if (measuring_) return;
   ep.beta = Lw.beta;
   ++launches_;
-  if (cfg_.backend == SM_BACKEND_TENSOR && Lw.gemm_ok) {
+  const double M = (double)in.B * Lw.g.out_size(in.H) * Lw.g.out_size(in.W);
+  const double K = (double)Lw.g.KH * Lw.g.KW * Lw.g.Cin;
+  const bool tc = cfg_.backend == SM_BACKEND_TENSOR && Lw.gemm_ok;
+  Scope sc(this, Lw.conv_key, tc ? "conv_gemm" : "conv_simt", 2.0 * M * K * Lw.g.Cout,
+           4.0 * ((double)in.numel() + M * Lw.g.Cout + K * Lw.g.Cout), st);
+  if (tc) {
     ep.alpha = Lw.alpha;
     launch_gemm_conv(in, Lw.g, Lw.w_hi, Lw.w_lo, Lw.cout_pad, ep, exact_ ? 2 : 1, num_sms_, st);
   } else {
@@ -496,10 +534,18 @@ Act Engine::backbone(const float* x, int B, int S, Arena& ar, bool keep, cudaStr
   const int So = (S - 7) / 2 + 1;
   Act p0 = alloc_act(ar, B, So, So, 64);
   const ConvW& stem = L(F + "conv1");
-  if (!measuring_) { launch_stem(x, B, S, stem.w_ref, ones_, stem.beta, p0, st); ++launches_; }
+  if (!measuring_) {
+    Scope sc(this, "stem", "stem", 2.0 * B * So * So * 64 * 147, 4.0 * B * (3.0 * S * S + 64.0 * So * So), st);
+    launch_stem(x, B, S, stem.w_ref, ones_, stem.beta, p0, st);
+    ++launches_;
+  }
   const int Sp = (So + 2 - 3) / 2 + 1;
   Act y = alloc_act(ar, B, Sp, Sp, 64);
-  if (!measuring_) { launch_maxpool3s2(p0, y, st); ++launches_; }
+  if (!measuring_) {
+    Scope sc(this, "maxpool", "pool", 0, 4.0 * (p0.numel() + y.numel()), st);
+    launch_maxpool3s2(p0, y, st);
+    ++launches_;
+  }
   if (keep) named_["p0"] = p0;
   const char* names[3] = {"layer1", "layer2", "layer3"};
   const int blocks[3] = {3, 4, 6};
@@ -569,8 +615,12 @@ void Engine::do_track(int slot0, int B, const float* x, float* cls, float* loc, 
     Act cs = conv(xf, L(P + "conv_search.0"), true, nullptr, search_arena_, st);
     Act corr = alloc_act(search_arena_, B, cs.H - 4, cs.W - 4, 256);
     const size_t off = ((size_t)br * cfg_.num_slots + slot0) * 25 * 256;
-    launch_xcorr_nhwc(cs, kcache_hi_ + off, exact_ ? kcache_lo_ + off : nullptr, 5, 5, corr, st);
-    ++launches_;
+    {
+      Scope sc(this, std::string(kCorrName[br]), "xcorr", 2.0 * 25 * corr.numel(),
+               4.0 * (cs.numel() + corr.numel() + (double)B * 25 * 256), st);
+      launch_xcorr_nhwc(cs, kcache_hi_ + off, exact_ ? kcache_lo_ + off : nullptr, 5, 5, corr, st);
+      ++launches_;
+    }
     named_[kCorrName[br]] = corr;
     if (br == 2 && !want_mask_head) break;
     Act h = conv(corr, L(P + "head.0"), true, nullptr, search_arena_, st);
@@ -592,6 +642,8 @@ F32T Engine::small(const F32T& a, const F32T* b, int Ho, const ConvW& Lw, bool r
                                   : static_cast<float*>(ar.alloc((size_t)a.B * Ho * Ho * Lw.g.Cout * sizeof(float)));
   SMK_CHECK(a.C == Lw.g.Cin && (b == nullptr || (b->C == a.C && b->H == a.H)), "small conv operand shapes");
   const int* map = updown_map(Ho, a.H);
+  Scope sc(this, Lw.conv_key, "refine_small", 2.0 * a.B * Ho * Ho * 9.0 * a.C * Lw.g.Cout,
+           4.0 * a.B * ((double)a.H * a.W * a.C * (b ? 2 : 1) + (double)Ho * Ho * Lw.g.Cout), st);
   launch_small_conv3x3_maps(a.p, b ? b->p : nullptr, a.B, a.H, a.W, Ho, Ho, a.C, Lw.g.Cout, map, map, Lw.w_ref, Lw.beta,
                             relu ? 1 : 0, out.p, st);
   ++launches_;
@@ -611,12 +663,18 @@ void Engine::do_refine(int B, const int32_t* pos, float* out, cudaStream_t st) {
   const Act& corr = named_["corr_mask"];
   // p3 = corr_feature[:, :, dy, dx]; out = deconv(p3)
   float* p3 = static_cast<float*>(ar.alloc((size_t)B * 256 * sizeof(float)));
-  launch_gather_corr(corr, pos, p3, st); ++launches_;
   F32T d = alloc_f32(ar, B, 15, 15, 32);
-  launch_deconv(p3, deconv_w_, deconv_b_, d.p, B, 256, 7200, 32, st); ++launches_;
+  {
+    Scope sc(this, "deconv", "refine_misc", 2.0 * B * 256 * 7200, 4.0 * (256.0 * 7200 + B * 7200.0), st);
+    launch_gather_corr(corr, pos, p3, st); ++launches_;
+    launch_deconv(p3, deconv_w_, deconv_b_, d.p, B, 256, 7200, 32, st); ++launches_;
+  }
   // level 2 (15x15): post0(up31(h2(out) + v2(p2)))
   Act c2 = alloc_act(ar, B, 15, 15, 512);
-  launch_refine_crop(p2, pos, 1, 4, 15, c2, st); ++launches_;
+  {
+    Scope sc(this, "crop_p2", "refine_misc", 0, 8.0 * c2.numel(), st);
+    launch_refine_crop(p2, pos, 1, 4, 15, c2, st); ++launches_;
+  }
   Act v2a = conv(c2, L(R + "v2.0"), true, nullptr, ar, st);
   F32T v2b = conv_f32(v2a, L(R + "v2.2"), true, ar, st);
   F32T h2a = small(d, nullptr, 15, L(R + "h2.0"), true, nullptr, ar, st);
@@ -624,7 +682,10 @@ void Engine::do_refine(int B, const int32_t* pos, float* out, cudaStream_t st) {
   F32T o0 = small(h2b, &v2b, 31, L(R + "post0"), false, nullptr, ar, st);
   // level 1 (31x31)
   Act c1 = alloc_act(ar, B, 31, 31, 256);
-  launch_refine_crop(p1, pos, 2, 8, 31, c1, st); ++launches_;
+  {
+    Scope sc(this, "crop_p1", "refine_misc", 0, 8.0 * c1.numel(), st);
+    launch_refine_crop(p1, pos, 2, 8, 31, c1, st); ++launches_;
+  }
   Act v1a = conv(c1, L(R + "v1.0"), true, nullptr, ar, st);
   F32T v1b = conv_f32(v1a, L(R + "v1.2"), true, ar, st);
   F32T h1a = small(o0, nullptr, 31, L(R + "h1.0"), true, nullptr, ar, st);
@@ -632,7 +693,10 @@ void Engine::do_refine(int B, const int32_t* pos, float* out, cudaStream_t st) {
   F32T o1 = small(h1b, &v1b, 61, L(R + "post1"), false, nullptr, ar, st);
   // level 0 (61x61)
   Act c0 = alloc_act(ar, B, 61, 61, 64);
-  launch_refine_crop(p0, pos, 4, 16, 61, c0, st); ++launches_;
+  {
+    Scope sc(this, "crop_p0", "refine_misc", 0, 8.0 * c0.numel(), st);
+    launch_refine_crop(p0, pos, 4, 16, 61, c0, st); ++launches_;
+  }
   F32T v0a = conv_f32(c0, L(R + "v0.0"), true, ar, st);
   F32T v0b = small(v0a, nullptr, 61, L(R + "v0.2"), true, nullptr, ar, st);
   F32T h0a = small(o1, nullptr, 61, L(R + "h0.0"), true, nullptr, ar, st);
@@ -663,6 +727,22 @@ void Engine::do_export(const char* what, float* out, int64_t* shape4, cudaStream
   const Act& a = it->second;
   if (shape4 != nullptr) { shape4[0] = a.B; shape4[1] = a.C; shape4[2] = a.H; shape4[3] = a.W; }
   if (out != nullptr) { launch_split_to_f32(a, out, st); ++launches_; }
+}
+
+std::string Engine::profile_dump() {
+  SMK_CUDA(cudaDeviceSynchronize());
+  std::string out;
+  for (auto& r : prof_) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    char line[512];
+    snprintf(line, sizeof line, "%s\t%s\t%.6f\t%.0f\t%.0f\n", r.name.c_str(), r.cat.c_str(), ms, r.flops, r.bytes);
+    out += line;
+    event_pool_.push_back(r.e0);
+    event_pool_.push_back(r.e1);
+  }
+  prof_.clear();
+  return out;
 }
 
 // ================================================================================================
@@ -866,6 +946,29 @@ int sm_export(sm_engine* e, const char* what, float* out, int64_t* shape4, void*
   SMK_CHECK(e && what, "null argument");
   e->impl->do_export(what, out, shape4, static_cast<cudaStream_t>(stream));
   SM_API_END
+}
+
+int sm_profile_enable(sm_engine* e, int32_t on) {
+  SM_API_BEGIN
+  SMK_CHECK(e, "null argument");
+  e->impl->set_profiling(on != 0);
+  SM_API_END
+}
+
+int64_t sm_profile_dump(sm_engine* e, char* buf, size_t cap) {
+  try {
+    if (!e) return -1;
+    static thread_local std::string pending;
+    if (pending.empty()) pending = e->impl->profile_dump();
+    if (buf == nullptr || cap <= pending.size()) return (int64_t)pending.size() + 1;
+    std::memcpy(buf, pending.c_str(), pending.size() + 1);
+    const int64_t n = (int64_t)pending.size();
+    pending.clear();
+    return n;
+  } catch (const std::exception& ex) {
+    smk::g_last_error = ex.what();
+    return -1;
+  }
 }
 
 int64_t sm_launch_count(const sm_engine* e) { return e ? e->impl->launches() : 0; }

@@ -201,6 +201,23 @@ class Custom:
             _lib.check(self._lib.sm_export(self._engine, what.encode(), out.data_ptr(), shape, self._stream()))
         return out
 
+    def profile(self, on: bool):
+        _lib.check(self._lib.sm_profile_enable(self._engine, int(on)))
+
+    def profile_dump(self):
+        """-> list of (name, category, ms, flops, bytes) for every launch since profiling was enabled."""
+        n = int(self._lib.sm_profile_dump(self._engine, None, 0))
+        if n < 0:
+            _lib.check(-1)
+        buf = C.create_string_buffer(n + 16)
+        if int(self._lib.sm_profile_dump(self._engine, buf, n + 16)) < 0:
+            _lib.check(-1)
+        rows = []
+        for line in buf.value.decode().splitlines():
+            name, cat, ms, fl, by = line.split("\t")
+            rows.append((name, cat, float(ms), float(fl), float(by)))
+        return rows
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.sm_launch_count(self._engine))
