@@ -46,6 +46,9 @@ struct Epilogue {
 struct GemmParams {
   CUtensorMap tmA[2];  // activations: hi / lo plane.  a_mode 0: 2D [M][Cin]; 1: im2col over NHWC
   CUtensorMap tmB[2];  // weights: hi / lo, 2D [Cout_pad][Ktot], K-major
+  CUtensorMap tmOut[2]; // staged epilogue: output planes [M][Cout], box 32 cols x 32 rows, 64B swizzle
+  CUtensorMap tmRes[2]; // staged epilogue: residual planes, same geometry
+  int staged;           // 1: epilogue goes smem -> TMA store (NHWC split outputs), residual via TMA load
   int M, Cout, Ho, Wo;
   int num_kb, cblks, KW;
   int stride, pad, dil;

@@ -39,7 +39,11 @@ template <int BLOCK_N, int NSPLIT>
 struct Cfg {
   static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = NSPLIT * (A_TILE_BYTES + B_TILE_BYTES);
-  static constexpr int RAW_STAGES = (SMEM_LIMIT - 2048) / STAGE_BYTES;
+  // epilogue staging: 4 warps x 2 buffers x NSPLIT planes x (32 rows x 64 B)
+  static constexpr int STG_TILE_BYTES = 32 * 64;
+  static constexpr int STG_WARP_BYTES = 2 * NSPLIT * STG_TILE_BYTES;
+  static constexpr int STG_BYTES = BLOCK_N >= 32 ? 4 * STG_WARP_BYTES : 0;
+  static constexpr int RAW_STAGES = (SMEM_LIMIT - 2048 - STG_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = RAW_STAGES > 6 ? 6 : RAW_STAGES;
   // 2 pipeline stages x NSPLIT accumulators (exact mode keeps the hi*hi sum and the 2^-11-sized cross terms in
   // separate TMEM accumulators: the tensor pipe truncates on every accumulate, so feeding small terms into the
@@ -50,7 +54,7 @@ struct Cfg {
   static_assert(2 * ACC_COLS <= 512, "TMEM capacity");
   static constexpr int CH = BLOCK_N < 32 ? 16 : 32;   // epilogue column chunk
   // one CTA per SM: keep the request above half of the SM's shared memory
-  static constexpr int SMEM_BYTES_RAW = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES_RAW = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int SMEM_BYTES = SMEM_BYTES_RAW < 120 * 1024 ? 120 * 1024 : SMEM_BYTES_RAW;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N constraint for M=128");
@@ -71,11 +75,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint8_t* stg_base = smem + STAGES * C::STAGE_BYTES;                      // 1024-aligned (stage sizes are)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + C::STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;                                       // [4 warps][2 buffers]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -93,6 +99,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 4);   // one arrival per epilogue warp
+    }
+    for (int a = 0; a < 8; ++a) mbar_init(&res_bar[a], 1);
+    if (p.staged) {
+      for (int i = 0; i < NSPLIT; ++i) {
+        tma_prefetch_desc(&p.tmOut[i]);
+        if (p.ep.res_hi != nullptr) tma_prefetch_desc(&p.tmRes[i]);
+      }
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -185,7 +198,131 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
     const Epilogue& ep = p.ep;
     const int HoWo = p.Ho * p.Wo;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    if constexpr (BLOCK_N >= 32) {
+      if (p.staged) {
+        // ---- staged path: TMEM -> registers -> 64B-swizzled smem -> TMA store; residual arrives by TMA load.
+        // Every warp owns 32 output rows and two staging buffers; loads run one 32-column chunk ahead.
+        uint8_t* stg = stg_base + quarter * C::STG_WARP_BYTES;
+        uint64_t* rbar = res_bar + quarter * 2;
+        const bool has_res = ep.res_hi != nullptr;
+        constexpr int CHUNKS = BLOCK_N / 32;
+        const int swz = (lane >> 1) & 3;                       // Swizzle<2,4,3>: 16B chunk ^= (row >> 1) & 3
+        uint8_t* my_row = stg + lane * 64;
+        uint32_t kchunk = 0;
+        if (has_res && lane == 0 && blockIdx.x < num_tiles) {
+          const int m0 = (blockIdx.x / p.n_tiles) * BLOCK_M + quarter * 32;
+          const int n0 = (blockIdx.x % p.n_tiles) * BLOCK_N;
+          mbar_arrive_expect_tx(&rbar[0], NSPLIT * C::STG_TILE_BYTES);
+#pragma unroll
+          for (int s = 0; s < NSPLIT; ++s) tma_load_2d(stg + s * C::STG_TILE_BYTES, &p.tmRes[s], &rbar[0], n0, m0);
+        }
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+          const int acc = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          const int m0 = (tile / p.n_tiles) * BLOCK_M + quarter * 32;
+          const int n0 = (tile % p.n_tiles) * BLOCK_N;
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          tcgen05_fence_after();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * C::ACC_COLS;
+#pragma unroll 1
+          for (int c = 0; c < CHUNKS; ++c, ++kchunk) {
+            const int b = kchunk & 1;
+            uint8_t* buf = stg + b * NSPLIT * C::STG_TILE_BYTES;
+            if (lane == 0) {
+              // the other buffer was stored one chunk ago: once its smem has been read it can take the
+              // residual of the next chunk; this buffer (stored two chunks ago) is then free as well
+              tma_store_wait_read<0>();
+              if (has_res) {
+                int nt = tile, nc = c + 1;
+                if (nc == CHUNKS) { nc = 0; nt = tile + gridDim.x; }
+                if (nt < num_tiles) {
+                  const int nm0 = (nt / p.n_tiles) * BLOCK_M + quarter * 32;
+                  const int nn0 = (nt % p.n_tiles) * BLOCK_N + nc * 32;
+                  uint8_t* nbuf = stg + (b ^ 1) * NSPLIT * C::STG_TILE_BYTES;
+                  mbar_arrive_expect_tx(&rbar[b ^ 1], NSPLIT * C::STG_TILE_BYTES);
+#pragma unroll
+                  for (int s = 0; s < NSPLIT; ++s)
+                    tma_load_2d(nbuf + s * C::STG_TILE_BYTES, &p.tmRes[s], &rbar[b ^ 1], nn0, nm0);
+                }
+              }
+            }
+            __syncwarp();
+            uint32_t r[32];
+            tmem_ld_chunk<32>(taddr + c * 32, r);
+            if constexpr (NSPLIT == 2) {
+              uint32_t r2[32];
+              tmem_ld_chunk<32>(taddr + BLOCK_N + c * 32, r2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+            } else {
+              tmem_ld_wait();
+            }
+            const int n = n0 + c * 32;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 al = __ldg(reinterpret_cast<const float4*>(ep.alpha + n + j));
+              const float4 be = __ldg(reinterpret_cast<const float4*>(ep.beta + n + j));
+              v[j + 0] = fmaf(__uint_as_float(r[j + 0]), al.x, be.x);
+              v[j + 1] = fmaf(__uint_as_float(r[j + 1]), al.y, be.y);
+              v[j + 2] = fmaf(__uint_as_float(r[j + 2]), al.z, be.z);
+              v[j + 3] = fmaf(__uint_as_float(r[j + 3]), al.w, be.w);
+            }
+            if (has_res) {
+              mbar_wait(&rbar[b], (kchunk >> 1) & 1);
+#pragma unroll
+              for (int s = 0; s < NSPLIT; ++s) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 h = *reinterpret_cast<const uint4*>(buf + s * C::STG_TILE_BYTES + lane * 64 + ((j ^ swz) << 4));
+                  const __half2* hh = reinterpret_cast<const __half2*>(&h);
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) {
+                    const float2 f = __half22float2(hh[t]);
+                    v[8 * j + 2 * t] += f.x;
+                    v[8 * j + 2 * t + 1] += f.y;
+                  }
+                }
+              }
+            }
+            if (ep.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 h, l;
+              __half2* hh = reinterpret_cast<__half2*>(&h);
+              __half2* ll = reinterpret_cast<__half2*>(&l);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const __half2 hv = __floats2half2_rn(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]);
+                hh[t] = hv;
+                const float2 hf = __half22float2(hv);
+                ll[t] = __floats2half2_rn(v[8 * j + 2 * t] - hf.x, v[8 * j + 2 * t + 1] - hf.y);
+              }
+              *reinterpret_cast<uint4*>(buf + lane * 64 + ((j ^ swz) << 4)) = h;
+              if constexpr (NSPLIT == 2) *reinterpret_cast<uint4*>(buf + C::STG_TILE_BYTES + lane * 64 + ((j ^ swz) << 4)) = l;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+              for (int s = 0; s < NSPLIT; ++s) tma_store_2d(&p.tmOut[s], buf + s * C::STG_TILE_BYTES, n, m0);
+              tma_store_commit();
+            }
+          }
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        if (lane == 0) tma_store_wait_all();
+        (void)my_row;
+        it = -1;   // tiles consumed
+      }
+    }
+    for (int tile = blockIdx.x; it >= 0 && tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m0 = (tile / p.n_tiles) * BLOCK_M;
@@ -343,6 +480,19 @@ CUtensorMap make_map_2d(const __half* base, uint64_t inner, uint64_t outer, uint
   return m;
 }
 
+CUtensorMap make_map_epilogue(const __half* base, uint64_t cout, uint64_t m) {
+  CUtensorMap t;
+  cuuint64_t dims[2] = {cout, m};
+  cuuint64_t strides[1] = {cout * sizeof(__half)};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = driver_api().tiled(&t, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides,
+                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SMK_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (epilogue) failed, code " + std::to_string((int)r));
+  return t;
+}
+
 CUtensorMap make_map_im2col(const __half* base, const Act& in, const ConvGeom& g) {
   CUtensorMap m;
   cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.B};
@@ -423,6 +573,22 @@ void launch_gemm_conv(const Act& in, const ConvGeom& g, const __half* w_hi, cons
     p.tmB[s] = make_map_2d(w, ktot, cout_pad, BLOCK_K, block_n);
   }
   if (nsplit == 1) { p.tmA[1] = p.tmA[0]; p.tmB[1] = p.tmB[0]; }
+  p.staged = (ep.out_mode == OUT_NHWC_SPLIT && block_n >= 32 && g.Cout % 32 == 0) ? 1 : 0;
+  if (p.staged) {
+    SMK_CHECK(nsplit == 1 || ep.out_lo != nullptr, "exact mode writes both planes");
+    for (int s = 0; s < nsplit; ++s) {
+      p.tmOut[s] = make_map_epilogue(s == 0 ? ep.out_hi : ep.out_lo, g.Cout, p.M);
+      if (ep.res_hi != nullptr) {
+        SMK_CHECK(nsplit == 1 || ep.res_lo != nullptr, "exact mode residual needs both planes");
+        p.tmRes[s] = make_map_epilogue(s == 0 ? ep.res_hi : ep.res_lo, g.Cout, p.M);
+      }
+    }
+    if (nsplit == 1) p.tmOut[1] = p.tmOut[0];
+    if (ep.res_hi == nullptr) { p.tmRes[0] = p.tmOut[0]; p.tmRes[1] = p.tmOut[1]; }
+    else if (nsplit == 1) p.tmRes[1] = p.tmRes[0];
+  } else {
+    p.tmOut[0] = p.tmOut[1] = p.tmRes[0] = p.tmRes[1] = p.tmB[0];
+  }
 
 #define SMK_DISPATCH(BN)                                             \
   case BN:                                                           \

@@ -136,28 +136,53 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
   }
 }
 
-// 3x3 stride-2 pad-1 max-pool over NHWC split planes (resnet.py:158,221); thread = pixel x channel pair.
+// 3x3 stride-2 pad-1 max-pool over NHWC split planes (resnet.py:158,221); thread = pixel x 8 channels
+// (one 16-byte load per plane and tap).
 __global__ void maxpool_kernel(Act in, Act out) {
-  const size_t total = out.numel() / 2;
-  const int c2n = out.C / 2;
+  const size_t total = out.numel() / 8;
+  const int c8n = out.C / 8;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int c = (idx % c2n) * 2;
-    const size_t m = idx / c2n;
+    const int c = (idx % c8n) * 8;
+    const size_t m = idx / c8n;
     const int wo = m % out.W, ho = (m / out.W) % out.H;
     const int b = m / ((size_t)out.W * out.H);
-    float2 best = make_float2(-INFINITY, -INFINITY);
+    float best[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
     for (int r = 0; r < 3; ++r) {
       const int hi_ = ho * 2 - 1 + r;
       if (hi_ < 0 || hi_ >= in.H) continue;
       for (int s = 0; s < 3; ++s) {
         const int wi = wo * 2 - 1 + s;
         if (wi < 0 || wi >= in.W) continue;
-        const float2 v = split_load2(in.hi, in.lo, (((size_t)b * in.H + hi_) * in.W + wi) * in.C + c);
-        best.x = fmaxf(best.x, v.x);
-        best.y = fmaxf(best.y, v.y);
+        const size_t src = (((size_t)b * in.H + hi_) * in.W + wi) * in.C + c;
+        const uint4 h = *reinterpret_cast<const uint4*>(in.hi + src);
+        const __half2* hh = reinterpret_cast<const __half2*>(&h);
+        float v[8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { const float2 f = __half22float2(hh[t]); v[2 * t] = f.x; v[2 * t + 1] = f.y; }
+        if (in.lo != nullptr) {
+          const uint4 l = *reinterpret_cast<const uint4*>(in.lo + src);
+          const __half2* ll = reinterpret_cast<const __half2*>(&l);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) { const float2 f = __half22float2(ll[t]); v[2 * t] += f.x; v[2 * t + 1] += f.y; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], v[j]);
       }
     }
-    split_store2(out.hi, out.lo, m * out.C + c, best);
+    uint4 h, l;
+    __half2* hh = reinterpret_cast<__half2*>(&h);
+    __half2* ll = reinterpret_cast<__half2*>(&l);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const __half2 hv = __floats2half2_rn(best[2 * t], best[2 * t + 1]);
+      hh[t] = hv;
+      const float2 hf = __half22float2(hv);
+      ll[t] = __floats2half2_rn(best[2 * t] - hf.x, best[2 * t + 1] - hf.y);
+    }
+    *reinterpret_cast<uint4*>(out.hi + m * out.C + c) = h;
+    if (out.lo != nullptr) *reinterpret_cast<uint4*>(out.lo + m * out.C + c) = l;
   }
 }
 
@@ -442,7 +467,7 @@ void launch_stem(const float* x, int B, int S, const float* w, const float* alph
 
 void launch_maxpool3s2(const Act& in, Act out, cudaStream_t st) {
   SMK_CHECK(out.H == (in.H + 2 - 3) / 2 + 1 && out.C == in.C && out.B == in.B, "maxpool output shape");
-  maxpool_kernel<<<grid_for(out.numel() / 2, 256), 256, 0, st>>>(in, out);
+  maxpool_kernel<<<grid_for(out.numel() / 8, 256), 256, 0, st>>>(in, out);
   SMK_CUDA(cudaGetLastError());
 }
 

@@ -175,18 +175,19 @@ class Custom:
     @torch.no_grad()
     def track_refine(self, pos):
         B = self._last_B
-        if isinstance(pos, torch.Tensor):
-            p = pos.to(self._device, torch.int32).reshape(-1, 2)
+        R = self.score_size
+        if isinstance(pos, torch.Tensor) and pos.is_cuda:
+            p = pos.to(self._device, torch.int32).reshape(-1, 2)     # device tensor: no host sync, caller's contract
         else:
-            p = torch.as_tensor(np.asarray(pos, dtype=np.int64).reshape(-1, 2).astype(np.int32), device=self._device)
+            host = np.asarray(pos.cpu() if isinstance(pos, torch.Tensor) else pos, dtype=np.int64).reshape(-1, 2)
+            if ((host < 0) | (host >= R)).any():
+                raise IndexError(f"refine position out of range [0,{R})")
+            p = torch.as_tensor(host.astype(np.int32), device=self._device)
         if p.shape[0] == 1 and B > 1:
             p = p.expand(B, 2)
         p = p.contiguous()
         if p.shape[0] != B:
             raise ValueError(f"pos has {p.shape[0]} rows, last track had batch {B}")
-        R = self.score_size
-        if bool(((p < 0) | (p >= R)).any()):
-            raise IndexError(f"refine position out of range [0,{R})")
         out = torch.empty(B, 127 * 127, device=self._device, dtype=torch.float32)
         with torch.cuda.device(self._device):
             _lib.check(self._lib.sm_refine(self._engine, B, p.data_ptr(), out.data_ptr(), self._stream()))
