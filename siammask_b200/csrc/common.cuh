@@ -42,19 +42,33 @@ struct Epilogue {
   int relu = 0;
 };
 
-// Parameters of the tcgen05 implicit-GEMM convolution kernel (passed by value, __grid_constant__).
-struct GemmParams {
-  CUtensorMap tmA[2];  // activations: hi / lo plane.  a_mode 0: 2D [M][Cin]; 1: im2col over NHWC
-  CUtensorMap tmB[2];  // weights: hi / lo, 2D [Cout_pad][Ktot], K-major
-  CUtensorMap tmOut[2]; // staged epilogue: output planes [M][Cout], box 32 cols x 32 rows, 64B swizzle
-  CUtensorMap tmRes[2]; // staged epilogue: residual planes, same geometry
-  int staged;           // 1: epilogue goes smem -> TMA store (NHWC split outputs), residual via TMA load
-  int M, Cout, Ho, Wo;
+// One K-segment of the implicit GEMM (see conv_gemm_sm100.cu).
+struct GemmSegment {
+  CUtensorMap tmA[2];  // hi / lo plane.  kind 0, mode 0: 2D [M][Cin]; mode 1: im2col over NHWC; kind 1: residual [M][Cout]
+  int kind;            // 0: convolution segment, 1: identity (residual) segment
+  int mode;
   int num_kb, cblks, KW;
   int stride, pad, dil;
-  int a_mode;
+  int b_col0;          // first column of this segment inside the packed weight matrix
+};
+
+// Parameters of the tcgen05 implicit-GEMM convolution kernel (passed by value, __grid_constant__).
+struct GemmParams {
+  GemmSegment seg[2];
+  int nseg;
+  CUtensorMap tmB[2];   // weights: hi / lo, 2D [Cout_pad][w_ld], K-major
+  CUtensorMap tmOut[2]; // staged epilogue: output planes [M][Cout], box 32 cols x 32 rows, 64B swizzle
+  int M, Cout, Ho, Wo;
   int n_tiles, m_tiles;
+  int staged;           // 1: epilogue goes smem -> TMA store (NHWC split outputs)
   Epilogue ep;
+};
+
+// A convolution input for the GEMM launcher: activation + geometry + where its weights start in the matrix.
+struct GemmInput {
+  Act in;
+  ConvGeom g;
+  int w_col0;
 };
 
 struct CudaError : std::runtime_error {
@@ -80,6 +94,11 @@ struct CudaError : std::runtime_error {
 bool gemm_conv_supported(const ConvGeom& g);
 void launch_gemm_conv(const Act& in, const ConvGeom& g, const __half* w_hi, const __half* w_lo, int cout_pad,
                       const Epilogue& ep, int nsplit, int num_sms, cudaStream_t st);
+// General form: 1-2 conv segments accumulating into the same output, optional identity (residual) segment whose
+// diag(2^e) block starts at weight column res_col0 (< 0: none).  w_ld = row length of the weight matrix.
+void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, int res_col0, const __half* w_hi,
+                       const __half* w_lo, int cout_pad, int w_ld, const Epilogue& ep, int nsplit, int num_sms,
+                       cudaStream_t st);
 
 // simt_kernels.cu
 void launch_ref_conv(const Act& in, const ConvGeom& g, const float* w_krsc_cout, const Epilogue& ep,

@@ -17,6 +17,11 @@
 //   NHWC split-fp16 planes, NHWC fp32, or NCHW fp32 (the boundary layout of the reference's outputs,
 //   tools/test.py:205-206) — TMEM lanes are pixels, so NCHW stores are coalesced across the warp.
 //
+// * K may consist of up to two SEGMENTS that accumulate into the same tile: (conv over input 0) + (conv over
+//   input 1) fuses a bottleneck's downsample branch with its conv3, and an IDENTITY segment
+//   acc += residual * diag(2^e) streams the residual tensor through the same TMA/MMA pipeline (one extra
+//   k-block per 64 output columns) instead of stalling the epilogue on it.
+//
 // Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one lane),
 // warps 2..5 = epilogue.  Persistent: grid = min(tiles, SMs), static round-robin over (m_tile, n_tile).
 #include "common.cuh"
@@ -80,8 +85,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* res_bar = tempty_bar + 2;                                       // [4 warps][2 buffers]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSPLIT; ++i) {
-      tma_prefetch_desc(&p.tmA[i]);
+      for (int sgi = 0; sgi < p.nseg; ++sgi) tma_prefetch_desc(&p.seg[sgi].tmA[i]);
       tma_prefetch_desc(&p.tmB[i]);
     }
     for (int s = 0; s < STAGES; ++s) {
@@ -100,13 +104,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 4);   // one arrival per epilogue warp
     }
-    for (int a = 0; a < 8; ++a) mbar_init(&res_bar[a], 1);
-    if (p.staged) {
-      for (int i = 0; i < NSPLIT; ++i) {
-        tma_prefetch_desc(&p.tmOut[i]);
-        if (p.ep.res_hi != nullptr) tma_prefetch_desc(&p.tmRes[i]);
-      }
-    }
+    if (p.staged)
+      for (int i = 0; i < NSPLIT; ++i) tma_prefetch_desc(&p.tmOut[i]);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -126,35 +125,52 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.n_tiles) * BLOCK_M;
       const int n0 = (tile % p.n_tiles) * BLOCK_N;
-      int wb = 0, hb = 0, nb = 0;
-      if (p.a_mode == 1) {
-        const int q = m0 % p.Wo;
-        const int t = m0 / p.Wo;
-        wb = q * p.stride - p.pad;
-        hb = (t % p.Ho) * p.stride - p.pad;
-        nb = t / p.Ho;
-      }
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* st = smem + stage * C::STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-        const int tap = kb / p.cblks;
-        const int c0 = (kb - tap * p.cblks) * BLOCK_K;
+      const int q = m0 % p.Wo;
+      const int t = m0 / p.Wo;
+      const int pq = t % p.Ho;
+      const int nb = t / p.Ho;
+      for (int sgi = 0; sgi < p.nseg; ++sgi) {
+        const GemmSegment& sg = p.seg[sgi];
+        if (sg.kind == 1) {
+          // identity segment: A = residual tile [128 rows x 64 cols] (K-major), B = diag(2^e) block (hi plane only)
+#pragma unroll 1
+          for (int kb = 0; kb < BLOCK_N / BLOCK_K; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * C::STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], NSPLIT * A_TILE_BYTES + C::B_TILE_BYTES);
 #pragma unroll
-        for (int s = 0; s < NSPLIT; ++s) {
-          uint8_t* a_dst = st + s * A_TILE_BYTES;
-          if (p.a_mode == 0) {
-            tma_load_2d(a_dst, &p.tmA[s], &full_bar[stage], c0, m0);
-          } else {
-            const int r = tap / p.KW;
-            const int sx = tap - r * p.KW;
-            tma_load_im2col_4d(a_dst, &p.tmA[s], &full_bar[stage], c0, wb, hb, nb,
-                               static_cast<uint16_t>(sx * p.dil), static_cast<uint16_t>(r * p.dil));
+            for (int s = 0; s < NSPLIT; ++s)
+              tma_load_2d(st + s * A_TILE_BYTES, &sg.tmA[s], &full_bar[stage], n0 + kb * BLOCK_K, m0);
+            tma_load_2d(st + NSPLIT * A_TILE_BYTES, &p.tmB[0], &full_bar[stage], sg.b_col0 + n0 + kb * BLOCK_K, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          uint8_t* b_dst = st + NSPLIT * A_TILE_BYTES + s * C::B_TILE_BYTES;
-          tma_load_2d(b_dst, &p.tmB[s], &full_bar[stage], kb * BLOCK_K, n0);
+          continue;
         }
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        const int wb = q * sg.stride - sg.pad;
+        const int hb = pq * sg.stride - sg.pad;
+#pragma unroll 1
+        for (int kb = 0; kb < sg.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * C::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          const int tap = kb / sg.cblks;
+          const int c0 = (kb - tap * sg.cblks) * BLOCK_K;
+#pragma unroll
+          for (int s = 0; s < NSPLIT; ++s) {
+            uint8_t* a_dst = st + s * A_TILE_BYTES;
+            if (sg.mode == 0) {
+              tma_load_2d(a_dst, &sg.tmA[s], &full_bar[stage], c0, m0);
+            } else {
+              const int r = tap / sg.KW;
+              const int sx = tap - r * sg.KW;
+              tma_load_im2col_4d(a_dst, &sg.tmA[s], &full_bar[stage], c0, wb, hb, nb,
+                                 static_cast<uint16_t>(sx * sg.dil), static_cast<uint16_t>(r * sg.dil));
+            }
+            uint8_t* b_dst = st + NSPLIT * A_TILE_BYTES + s * C::B_TILE_BYTES;
+            tma_load_2d(b_dst, &p.tmB[s], &full_bar[stage], sg.b_col0 + kb * BLOCK_K, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (threadIdx.x == 32) {
@@ -169,27 +185,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * C::ACC_COLS;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        tcgen05_fence_after();
-        const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
-        const uint32_t b_hi = a_hi + NSPLIT * A_TILE_BYTES;
+      uint32_t acc_main = 0, acc_lo = 0;     // 0 on the first MMA into each accumulator of this tile
+      for (int sgi = 0; sgi < p.nseg; ++sgi) {
+        const GemmSegment& sg = p.seg[sgi];
+        const bool ident = sg.kind == 1;
+        const int nkb = ident ? BLOCK_N / BLOCK_K : sg.num_kb;
+        const bool last_seg = sgi == p.nseg - 1;
+#pragma unroll 1
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t b_hi = a_hi + NSPLIT * A_TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          const uint32_t koff = k * UMMA_K * 2;   // bytes along K inside the 128B swizzle row
-          const uint64_t da_hi = umma_desc_kmajor_sw128(a_hi + koff);
-          const uint64_t db_hi = umma_desc_kmajor_sw128(b_hi + koff);
-          umma_f16(tmem_d, da_hi, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-          if constexpr (NSPLIT == 2) {
-            const uint64_t da_lo = umma_desc_kmajor_sw128(a_hi + A_TILE_BYTES + koff);
-            const uint64_t db_lo = umma_desc_kmajor_sw128(b_hi + C::B_TILE_BYTES + koff);
-            umma_f16(tmem_d + BLOCK_N, da_lo, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_f16(tmem_d + BLOCK_N, da_hi, db_lo, idesc, 1u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint32_t koff = k * UMMA_K * 2;   // bytes along K inside the 128B swizzle row
+            const uint64_t da_hi = umma_desc_kmajor_sw128(a_hi + koff);
+            const uint64_t db_hi = umma_desc_kmajor_sw128(b_hi + koff);
+            umma_f16(tmem_d, da_hi, db_hi, idesc, acc_main);
+            acc_main = 1;
+            if constexpr (NSPLIT == 2) {
+              const uint64_t da_lo = umma_desc_kmajor_sw128(a_hi + A_TILE_BYTES + koff);
+              umma_f16(tmem_d + BLOCK_N, da_lo, db_hi, idesc, acc_lo);
+              acc_lo = 1;
+              if (!ident) {
+                const uint64_t db_lo = umma_desc_kmajor_sw128(b_hi + C::B_TILE_BYTES + koff);
+                umma_f16(tmem_d + BLOCK_N, da_hi, db_lo, idesc, 1u);
+              }
+            }
           }
+          umma_commit(&empty_bar[stage]);                                   // smem slot free once these MMAs retire
+          if (last_seg && kb == nkb - 1) umma_commit(&tfull_bar[acc]);      // accumulator complete
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
-        if (kb == p.num_kb - 1) umma_commit(&tfull_bar[acc]); // accumulator complete
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= 2) {
@@ -200,22 +228,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
     int it = 0;
     if constexpr (BLOCK_N >= 32) {
       if (p.staged) {
-        // ---- staged path: TMEM -> registers -> 64B-swizzled smem -> TMA store; residual arrives by TMA load.
-        // Every warp owns 32 output rows and two staging buffers; loads run one 32-column chunk ahead.
+        // ---- staged path: TMEM -> registers -> 64B-swizzled smem -> TMA store.  Every warp owns 32 output rows
+        // and two staging buffers, so the store of chunk k overlaps the math of chunk k+1.  (A residual, if any,
+        // has already been accumulated by the identity K-segment.)
         uint8_t* stg = stg_base + quarter * C::STG_WARP_BYTES;
-        uint64_t* rbar = res_bar + quarter * 2;
-        const bool has_res = ep.res_hi != nullptr;
         constexpr int CHUNKS = BLOCK_N / 32;
         const int swz = (lane >> 1) & 3;                       // Swizzle<2,4,3>: 16B chunk ^= (row >> 1) & 3
-        uint8_t* my_row = stg + lane * 64;
         uint32_t kchunk = 0;
-        if (has_res && lane == 0 && blockIdx.x < num_tiles) {
-          const int m0 = (blockIdx.x / p.n_tiles) * BLOCK_M + quarter * 32;
-          const int n0 = (blockIdx.x % p.n_tiles) * BLOCK_N;
-          mbar_arrive_expect_tx(&rbar[0], NSPLIT * C::STG_TILE_BYTES);
-#pragma unroll
-          for (int s = 0; s < NSPLIT; ++s) tma_load_2d(stg + s * C::STG_TILE_BYTES, &p.tmRes[s], &rbar[0], n0, m0);
-        }
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
           const int acc = it & 1;
           const uint32_t acc_phase = (it >> 1) & 1;
@@ -226,27 +245,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * C::ACC_COLS;
 #pragma unroll 1
           for (int c = 0; c < CHUNKS; ++c, ++kchunk) {
-            const int b = kchunk & 1;
-            uint8_t* buf = stg + b * NSPLIT * C::STG_TILE_BYTES;
-            if (lane == 0) {
-              // the other buffer was stored one chunk ago: once its smem has been read it can take the
-              // residual of the next chunk; this buffer (stored two chunks ago) is then free as well
-              tma_store_wait_read<0>();
-              if (has_res) {
-                int nt = tile, nc = c + 1;
-                if (nc == CHUNKS) { nc = 0; nt = tile + gridDim.x; }
-                if (nt < num_tiles) {
-                  const int nm0 = (nt / p.n_tiles) * BLOCK_M + quarter * 32;
-                  const int nn0 = (nt % p.n_tiles) * BLOCK_N + nc * 32;
-                  uint8_t* nbuf = stg + (b ^ 1) * NSPLIT * C::STG_TILE_BYTES;
-                  mbar_arrive_expect_tx(&rbar[b ^ 1], NSPLIT * C::STG_TILE_BYTES);
-#pragma unroll
-                  for (int s = 0; s < NSPLIT; ++s)
-                    tma_load_2d(nbuf + s * C::STG_TILE_BYTES, &p.tmRes[s], &rbar[b ^ 1], nn0, nm0);
-                }
-              }
-            }
-            __syncwarp();
+            uint8_t* buf = stg + (kchunk & 1) * NSPLIT * C::STG_TILE_BYTES;
             uint32_t r[32];
             tmem_ld_chunk<32>(taddr + c * 32, r);
             if constexpr (NSPLIT == 2) {
@@ -269,27 +268,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
               v[j + 2] = fmaf(__uint_as_float(r[j + 2]), al.z, be.z);
               v[j + 3] = fmaf(__uint_as_float(r[j + 3]), al.w, be.w);
             }
-            if (has_res) {
-              mbar_wait(&rbar[b], (kchunk >> 1) & 1);
-#pragma unroll
-              for (int s = 0; s < NSPLIT; ++s) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint4 h = *reinterpret_cast<const uint4*>(buf + s * C::STG_TILE_BYTES + lane * 64 + ((j ^ swz) << 4));
-                  const __half2* hh = reinterpret_cast<const __half2*>(&h);
-#pragma unroll
-                  for (int t = 0; t < 4; ++t) {
-                    const float2 f = __half22float2(hh[t]);
-                    v[8 * j + 2 * t] += f.x;
-                    v[8 * j + 2 * t + 1] += f.y;
-                  }
-                }
-              }
-            }
             if (ep.relu) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
+            // this buffer was handed to the TMA two chunks ago: wait until that store has read it
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 h, l;
@@ -318,7 +303,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
         if (lane == 0) tma_store_wait_all();
-        (void)my_row;
         it = -1;   // tiles consumed
       }
     }
@@ -543,52 +527,89 @@ int gemm_cout_pad(int cout) {
 
 void launch_gemm_conv(const Act& in, const ConvGeom& g, const __half* w_hi, const __half* w_lo, int cout_pad,
                       const Epilogue& ep, int nsplit, int num_sms, cudaStream_t st) {
-  SMK_CHECK(gemm_conv_supported(g), "Cin must be a multiple of 64 for the tensor-core conv");
-  SMK_CHECK(in.C == g.Cin, "input channels mismatch");
-  SMK_CHECK(nsplit == 1 || (in.lo != nullptr && w_lo != nullptr), "exact mode needs lo planes");
-  const int Ho = g.out_size(in.H), Wo = g.out_size(in.W);
+  GemmInput gi{in, g, 0};
+  launch_gemm_multi(&gi, 1, nullptr, -1, w_hi, w_lo, cout_pad, g.KH * g.KW * g.Cin, ep, nsplit, num_sms, st);
+}
+
+void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, int res_col0, const __half* w_hi,
+                       const __half* w_lo, int cout_pad, int w_ld, const Epilogue& ep_in, int nsplit, int num_sms,
+                       cudaStream_t st) {
+  SMK_CHECK(nconv >= 1 && nconv <= 2, "1 or 2 convolution segments");
+  SMK_CHECK(nconv + (residual != nullptr ? 1 : 0) <= 2, "at most two K segments");
+  Epilogue ep = ep_in;
+  const ConvGeom& g0 = convs[0].g;
+  const Act& in0 = convs[0].in;
+  const int Ho = g0.out_size(in0.H), Wo = g0.out_size(in0.W);
   GemmParams p;
-  p.M = in.B * Ho * Wo;
-  p.Cout = g.Cout;
+  p.M = in0.B * Ho * Wo;
+  p.Cout = g0.Cout;
   p.Ho = Ho;
   p.Wo = Wo;
-  p.cblks = g.Cin / BLOCK_K;
-  p.num_kb = g.KH * g.KW * p.cblks;
-  p.KW = g.KW;
-  p.stride = g.stride;
-  p.pad = g.pad;
-  p.dil = g.dil;
-  p.a_mode = (g.KH == 1 && g.KW == 1 && g.stride == 1 && g.pad == 0) ? 0 : 1;
   const int block_n = cout_pad < 256 ? cout_pad : (nsplit == 2 ? 128 : 256);
   SMK_CHECK(cout_pad % block_n == 0, "cout_pad must be a multiple of the N tile");
-  if (ep.out_mode != OUT_NCHW_F32) SMK_CHECK(g.Cout == cout_pad, "NHWC outputs need Cout to match the padded tile width");
+  if (ep.out_mode != OUT_NCHW_F32) SMK_CHECK(g0.Cout == cout_pad, "NHWC outputs need Cout to match the padded tile width");
   p.n_tiles = cout_pad / block_n;
   p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-  p.ep = ep;
-  const uint64_t ktot = (uint64_t)g.KH * g.KW * g.Cin;
-  for (int s = 0; s < nsplit; ++s) {
-    const __half* a = s == 0 ? in.hi : in.lo;
-    const __half* w = s == 0 ? w_hi : w_lo;
-    p.tmA[s] = p.a_mode == 0 ? make_map_2d(a, g.Cin, (uint64_t)in.M(), BLOCK_K, BLOCK_M) : make_map_im2col(a, in, g);
-    p.tmB[s] = make_map_2d(w, ktot, cout_pad, BLOCK_K, block_n);
+  p.nseg = 0;
+  for (int i = 0; i < nconv; ++i) {
+    const ConvGeom& g = convs[i].g;
+    const Act& in = convs[i].in;
+    SMK_CHECK(gemm_conv_supported(g), "Cin must be a multiple of 64 for the tensor-core conv");
+    SMK_CHECK(in.C == g.Cin && g.Cout == g0.Cout && in.B == in0.B, "segment channels/batch mismatch");
+    SMK_CHECK(g.out_size(in.H) == Ho && g.out_size(in.W) == Wo, "segments must produce the same output size");
+    SMK_CHECK(nsplit == 1 || (in.lo != nullptr && w_lo != nullptr), "exact mode needs lo planes");
+    GemmSegment& sg = p.seg[p.nseg++];
+    sg.kind = 0;
+    sg.cblks = g.Cin / BLOCK_K;
+    sg.num_kb = g.KH * g.KW * sg.cblks;
+    sg.KW = g.KW;
+    sg.stride = g.stride;
+    sg.pad = g.pad;
+    sg.dil = g.dil;
+    sg.mode = (g.KH == 1 && g.KW == 1 && g.stride == 1 && g.pad == 0) ? 0 : 1;
+    sg.b_col0 = convs[i].w_col0;
+    SMK_CHECK(sg.b_col0 % BLOCK_K == 0 && sg.b_col0 + g.KH * g.KW * g.Cin <= w_ld, "weight column range");
+    for (int s = 0; s < nsplit; ++s) {
+      const __half* a = s == 0 ? in.hi : in.lo;
+      sg.tmA[s] = sg.mode == 0 ? make_map_2d(a, g.Cin, (uint64_t)in.M(), BLOCK_K, BLOCK_M) : make_map_im2col(a, in, g);
+    }
+    if (nsplit == 1) sg.tmA[1] = sg.tmA[0];
   }
-  if (nsplit == 1) { p.tmA[1] = p.tmA[0]; p.tmB[1] = p.tmB[0]; }
-  p.staged = (ep.out_mode == OUT_NHWC_SPLIT && block_n >= 32 && g.Cout % 32 == 0) ? 1 : 0;
+  bool ident = false;
+  if (residual != nullptr) {
+    // the residual rides the tensor pipe: needs the diag(2^e) block in the weights and 64-wide column blocks
+    SMK_CHECK(res_col0 >= 0 && res_col0 % BLOCK_K == 0 && res_col0 + g0.Cout <= w_ld && block_n % BLOCK_K == 0,
+              "identity segment needs a diagonal block in the packed weights");
+    SMK_CHECK(residual->C == g0.Cout && residual->M() == p.M, "residual shape");
+    SMK_CHECK(nsplit == 1 || residual->lo != nullptr, "exact mode residual needs both planes");
+    GemmSegment& sg = p.seg[p.nseg++];
+    sg.kind = 1;
+    sg.mode = 0;
+    sg.num_kb = block_n / BLOCK_K;
+    sg.cblks = sg.KW = sg.stride = sg.dil = 1;
+    sg.pad = 0;
+    sg.b_col0 = res_col0;
+    for (int s = 0; s < nsplit; ++s)
+      sg.tmA[s] = make_map_2d(s == 0 ? residual->hi : residual->lo, g0.Cout, (uint64_t)p.M, BLOCK_K, BLOCK_M);
+    if (nsplit == 1) sg.tmA[1] = sg.tmA[0];
+    ident = true;
+    ep.res_hi = ep.res_lo = nullptr;       // accumulated by the MMA, not by the epilogue
+  }
+  if (p.nseg == 1) p.seg[1] = p.seg[0];
+  for (int s = 0; s < nsplit; ++s) p.tmB[s] = make_map_2d(s == 0 ? w_hi : w_lo, (uint64_t)w_ld, cout_pad, BLOCK_K, block_n);
+  if (nsplit == 1) p.tmB[1] = p.tmB[0];
+  // NHWC split outputs go through smem + TMA stores; an epilogue-side residual (no diagonal block) needs the
+  // direct path
+  p.staged = (ep.out_mode == OUT_NHWC_SPLIT && block_n >= 32 && g0.Cout % 32 == 0 && ep.res_hi == nullptr) ? 1 : 0;
+  (void)ident;
   if (p.staged) {
     SMK_CHECK(nsplit == 1 || ep.out_lo != nullptr, "exact mode writes both planes");
-    for (int s = 0; s < nsplit; ++s) {
-      p.tmOut[s] = make_map_epilogue(s == 0 ? ep.out_hi : ep.out_lo, g.Cout, p.M);
-      if (ep.res_hi != nullptr) {
-        SMK_CHECK(nsplit == 1 || ep.res_lo != nullptr, "exact mode residual needs both planes");
-        p.tmRes[s] = make_map_epilogue(s == 0 ? ep.res_hi : ep.res_lo, g.Cout, p.M);
-      }
-    }
+    for (int s = 0; s < nsplit; ++s) p.tmOut[s] = make_map_epilogue(s == 0 ? ep.out_hi : ep.out_lo, g0.Cout, p.M);
     if (nsplit == 1) p.tmOut[1] = p.tmOut[0];
-    if (ep.res_hi == nullptr) { p.tmRes[0] = p.tmOut[0]; p.tmRes[1] = p.tmOut[1]; }
-    else if (nsplit == 1) p.tmRes[1] = p.tmRes[0];
   } else {
-    p.tmOut[0] = p.tmOut[1] = p.tmRes[0] = p.tmRes[1] = p.tmB[0];
+    p.tmOut[0] = p.tmOut[1] = p.tmB[0];
   }
+  p.ep = ep;
 
 #define SMK_DISPATCH(BN)                                             \
   case BN:                                                           \

@@ -31,6 +31,15 @@ struct ConvW {
   int cout_pad = 0;
   bool gemm_ok = false;
   std::string conv_key, bn_key;       // bn_key empty -> conv has a bias instead
+  // tensor-core weight matrix [cout_pad][w_ld]: columns [0,K) this conv, then optionally a second conv whose
+  // output is accumulated into the same tile (the bottleneck's downsample branch, fused with conv3) or a
+  // diag(2^e) block that lets the residual tensor ride the MMA pipeline (identity segment).
+  ConvGeom g2{};
+  std::string conv_key2, bn_key2;
+  bool fused2 = false, has_diag = false;
+  int w_ld = 0, col2 = 0, col_diag = -1;
+  size_t off_beta2 = 0;
+  float* beta2 = nullptr;             // beta of the fused form (sum of both branches' shifts)
   size_t off_whi = 0, off_wlo = 0, off_wref = 0, off_alpha = 0, off_beta = 0;
   __half* w_hi = nullptr;
   __half* w_lo = nullptr;
@@ -100,8 +109,10 @@ class Engine {
   // ---- schedule
   Act alloc_act(Arena& ar, int B, int H, int W, int C);
   F32T alloc_f32(Arena& ar, int B, int H, int W, int C);
-  Act conv(const Act& in, const ConvW& L, bool relu, const Act* res, Arena& ar, cudaStream_t st);
-  void conv_into(const Act& in, const ConvW& L, Epilogue ep, cudaStream_t st);
+  Act conv(const Act& in, const ConvW& L, bool relu, const Act* res, Arena& ar, cudaStream_t st,
+           const Act* in2 = nullptr);
+  void conv_into(const Act& in, const ConvW& L, Epilogue ep, cudaStream_t st, const Act* res = nullptr,
+                 const Act* in2 = nullptr);
   F32T conv_f32(const Act& in, const ConvW& L, bool relu, Arena& ar, cudaStream_t st);
   Act backbone(const float* x, int B, int S, Arena& ar, bool keep, cudaStream_t st);
   F32T small(const F32T& a, const F32T* b, int Ho, const ConvW& L, bool relu, float* out_override, Arena& ar,
@@ -190,6 +201,7 @@ ConvW& Engine::add_layer(const std::string& conv_key, const std::string& bn_key,
   w.bn_key = bn_key;
   w.gemm_ok = gemm_conv_supported(g);
   w.cout_pad = w.gemm_ok ? gemm_cout_pad(g.Cout) : g.Cout;
+  w.w_ld = g.KH * g.KW * g.Cin;
   layer_order_.push_back(conv_key);
   return layers_[conv_key] = w;
 }
@@ -216,7 +228,16 @@ void Engine::build_layer_table() {
       const int pad = dil > 1 ? dil : 2 - stride;   // Bottleneck.__init__, resnet.py:66-70
       add_layer(P + "conv1", P + "bn1", {inplanes, sp.planes, 1, 1, 1, 0, 1});
       add_layer(P + "conv2", P + "bn2", {sp.planes, sp.planes, 3, 3, stride, pad, dil});
-      add_layer(P + "conv3", P + "bn3", {sp.planes, sp.planes * 4, 1, 1, 1, 0, 1});
+      ConvW& c3 = add_layer(P + "conv3", P + "bn3", {sp.planes, sp.planes * 4, 1, 1, 1, 0, 1});
+      if (i == 0) {                       // out = relu(bn3(conv3(t)) + bn_ds(conv_ds(x))): one GEMM, K = K3 + Kds
+        const ConvW& ds = layers_[P + "downsample.0"];
+        c3.fused2 = true;
+        c3.g2 = ds.g;
+        c3.conv_key2 = ds.conv_key;
+        c3.bn_key2 = ds.bn_key;
+      } else {                            // out = relu(bn3(conv3(t)) + x): residual via the identity segment
+        c3.has_diag = true;
+      }
       inplanes = sp.planes * 4;
     }
   }
@@ -249,10 +270,14 @@ void Engine::assign_blob_layout() {
   for (const auto& k : layer_order_) {
     ConvW& w = layers_[k];
     const size_t K = (size_t)w.g.KH * w.g.KW * w.g.Cin;
+    w.w_ld = (int)K;
+    if (w.fused2) { w.col2 = w.w_ld; w.w_ld += w.g2.KH * w.g2.KW * w.g2.Cin; }
+    if (w.has_diag) { w.col_diag = w.w_ld; w.w_ld += w.g.Cout; }
     if (w.gemm_ok) {
-      w.off_whi = off; off = align_up(off + (size_t)w.cout_pad * K * sizeof(__half));
-      w.off_wlo = off; off = align_up(off + (size_t)w.cout_pad * K * sizeof(__half));
+      w.off_whi = off; off = align_up(off + (size_t)w.cout_pad * w.w_ld * sizeof(__half));
+      w.off_wlo = off; off = align_up(off + (size_t)w.cout_pad * w.w_ld * sizeof(__half));
     }
+    w.off_beta2 = off; off = align_up(off + (size_t)w.cout_pad * sizeof(float));
     w.off_wref = off;  off = align_up(off + K * w.g.Cout * sizeof(float));
     w.off_alpha = off; off = align_up(off + (size_t)w.cout_pad * sizeof(float));
     w.off_beta = off;  off = align_up(off + (size_t)w.cout_pad * sizeof(float));
@@ -290,6 +315,7 @@ Engine::Engine(const sm_config& cfg) : cfg_(cfg), exact_(cfg.precision == SM_PRE
     w.w_ref = reinterpret_cast<float*>(blob_ + w.off_wref);
     w.alpha = reinterpret_cast<float*>(blob_ + w.off_alpha);
     w.beta = reinterpret_cast<float*>(blob_ + w.off_beta);
+    w.beta2 = reinterpret_cast<float*>(blob_ + w.off_beta2);
   }
   ones_ = reinterpret_cast<float*>(blob_ + off_ones_);
   if (cfg_.with_mask) {
@@ -386,33 +412,49 @@ const float* find_tensor(const std::map<std::string, const sm_tensor_desc*>& sd,
 }
 }  // namespace
 
-void Engine::pack_layer(ConvW& L, const std::map<std::string, const sm_tensor_desc*>& sd, uint8_t* host) {
-  const ConvGeom& g = L.g;
-  const size_t K = (size_t)g.KH * g.KW * g.Cin;
-  const float* w = find_tensor(sd, L.conv_key + ".weight", K * g.Cout);   // OIHW
-  std::vector<double> scale(g.Cout, 1.0), shift(g.Cout, 0.0);
-  if (!L.bn_key.empty()) {
-    const float* gm = find_tensor(sd, L.bn_key + ".weight", g.Cout);
-    const float* bt = find_tensor(sd, L.bn_key + ".bias", g.Cout);
-    const float* mu = find_tensor(sd, L.bn_key + ".running_mean", g.Cout);
-    const float* var = find_tensor(sd, L.bn_key + ".running_var", g.Cout);
-    for (int n = 0; n < g.Cout; ++n) {
+namespace {
+// eval-mode BatchNorm folded to y = conv(x, w) * scale + shift (or the conv's own bias when there is no BN)
+void fold_affine(const std::map<std::string, const sm_tensor_desc*>& sd, const std::string& conv_key,
+                 const std::string& bn_key, int cout, std::vector<double>& scale, std::vector<double>& shift) {
+  scale.assign(cout, 1.0);
+  shift.assign(cout, 0.0);
+  if (!bn_key.empty()) {
+    const float* gm = find_tensor(sd, bn_key + ".weight", cout);
+    const float* bt = find_tensor(sd, bn_key + ".bias", cout);
+    const float* mu = find_tensor(sd, bn_key + ".running_mean", cout);
+    const float* var = find_tensor(sd, bn_key + ".running_var", cout);
+    for (int n = 0; n < cout; ++n) {
       scale[n] = (double)gm[n] / std::sqrt((double)var[n] + (double)BN_EPS);
       shift[n] = (double)bt[n] - (double)mu[n] * scale[n];
     }
   } else {
-    const float* b = find_tensor(sd, L.conv_key + ".bias", g.Cout);
-    for (int n = 0; n < g.Cout; ++n) shift[n] = b[n];
+    const float* b = find_tensor(sd, conv_key + ".bias", cout);
+    for (int n = 0; n < cout; ++n) shift[n] = b[n];
   }
+}
+}  // namespace
+
+void Engine::pack_layer(ConvW& L, const std::map<std::string, const sm_tensor_desc*>& sd, uint8_t* host) {
+  const ConvGeom& g = L.g;
+  const size_t K = (size_t)g.KH * g.KW * g.Cin;
+  const size_t K2 = L.fused2 ? (size_t)L.g2.KH * L.g2.KW * L.g2.Cin : 0;
+  const float* w = find_tensor(sd, L.conv_key + ".weight", K * g.Cout);   // OIHW
+  const float* w2 = L.fused2 ? find_tensor(sd, L.conv_key2 + ".weight", K2 * g.Cout) : nullptr;
+  std::vector<double> scale, shift, scale2, shift2;
+  fold_affine(sd, L.conv_key, L.bn_key, g.Cout, scale, shift);
+  if (L.fused2) fold_affine(sd, L.conv_key2, L.bn_key2, g.Cout, scale2, shift2);
   float* w_ref = reinterpret_cast<float*>(host + L.off_wref);
   float* alpha = reinterpret_cast<float*>(host + L.off_alpha);
   float* beta = reinterpret_cast<float*>(host + L.off_beta);
+  float* beta2 = reinterpret_cast<float*>(host + L.off_beta2);
   __half* w_hi = L.gemm_ok ? reinterpret_cast<__half*>(host + L.off_whi) : nullptr;
   __half* w_lo = L.gemm_ok ? reinterpret_cast<__half*>(host + L.off_wlo) : nullptr;
-  for (int n = 0; n < L.cout_pad; ++n) { alpha[n] = 0.f; beta[n] = 0.f; }
-  const int HW = g.KH * g.KW;
+  for (int n = 0; n < L.cout_pad; ++n) { alpha[n] = 0.f; beta[n] = 0.f; beta2[n] = 0.f; }
+  const int HW = g.KH * g.KW, HW2 = L.fused2 ? L.g2.KH * L.g2.KW : 0;
+  const size_t ld = (size_t)L.w_ld;
+  std::vector<float> row2(K2);
   for (int n = 0; n < g.Cout; ++n) {
-    // folded weight row (fp32), and its largest magnitude
+    // folded weight rows (fp32) and their largest magnitude
     float amax = 0.f;
     for (int c = 0; c < g.Cin; ++c)
       for (int t = 0; t < HW; ++t) {
@@ -420,28 +462,40 @@ void Engine::pack_layer(ConvW& L, const std::map<std::string, const sm_tensor_de
         w_ref[((size_t)t * g.Cin + c) * g.Cout + n] = fw;
         amax = std::max(amax, std::fabs(fw));
       }
+    for (int c = 0; c < (L.fused2 ? L.g2.Cin : 0); ++c)
+      for (int t = 0; t < HW2; ++t) {
+        const float fw = (float)((double)w2[((size_t)n * L.g2.Cin + c) * HW2 + t] * scale2[n]);
+        row2[(size_t)t * L.g2.Cin + c] = fw;
+        amax = std::max(amax, std::fabs(fw));
+      }
     beta[n] = (float)shift[n];
+    beta2[n] = (float)(shift[n] + (L.fused2 ? shift2[n] : 0.0));
     alpha[n] = 1.f;
     if (L.gemm_ok) {
-      // per-output-channel power-of-two scaling keeps hi AND lo fp16 parts in the normal range;
-      // the epilogue multiplies the accumulator back by 2^-e (exact).
+      // per-output-channel power-of-two scaling keeps hi AND lo fp16 parts in the normal range; the epilogue
+      // multiplies the accumulator back by 2^-e (exact).  |e| <= 14 so 2^e itself is a normal fp16 (diag block).
       int e = 0;
       if (amax > 0.f) e = (int)std::floor(std::log2(16384.0 / (double)amax));
-      e = std::max(-24, std::min(24, e));
-      const float up = std::ldexp(1.f, e);
+      e = std::max(-14, std::min(14, e));
       alpha[n] = std::ldexp(1.f, -e);
+      __half* rh = w_hi + (size_t)n * ld;
+      __half* rl = w_lo + (size_t)n * ld;
       for (int c = 0; c < g.Cin; ++c)
         for (int t = 0; t < HW; ++t) {
-          const float fw = w_ref[((size_t)t * g.Cin + c) * g.Cout + n] * up;
+          const float fw = std::ldexp(w_ref[((size_t)t * g.Cin + c) * g.Cout + n], e);
           const __half h = __float2half_rn(fw);
-          const size_t idx = ((size_t)n * HW + t) * g.Cin + c;
-          w_hi[idx] = h;
-          w_lo[idx] = __float2half_rn(fw - __half2float(h));
+          rh[(size_t)t * g.Cin + c] = h;
+          rl[(size_t)t * g.Cin + c] = __float2half_rn(fw - __half2float(h));
         }
+      for (size_t k = 0; k < K2; ++k) {
+        const float fw = std::ldexp(row2[k], e);
+        const __half h = __float2half_rn(fw);
+        rh[L.col2 + k] = h;
+        rl[L.col2 + k] = __float2half_rn(fw - __half2float(h));
+      }
+      if (L.has_diag) rh[L.col_diag + n] = __float2half_rn(std::ldexp(1.f, e));   // rest of the block stays 0
     }
   }
-  if (L.gemm_ok)
-    for (size_t i = (size_t)g.Cout * K; i < (size_t)L.cout_pad * K; ++i) { w_hi[i] = __float2half_rn(0.f); w_lo[i] = w_hi[i]; }
 }
 
 void Engine::load_weights(const sm_tensor_desc* t, int n) {
@@ -488,33 +542,50 @@ F32T Engine::alloc_f32(Arena& ar, int B, int H, int W, int C) {
   return t;
 }
 
-void Engine::conv_into(const Act& in, const ConvW& Lw, Epilogue ep, cudaStream_t st) {
+void Engine::conv_into(const Act& in, const ConvW& Lw, Epilogue ep, cudaStream_t st, const Act* res,
+                       const Act* in2) {
   if (measuring_) return;
   ep.beta = Lw.beta;
   ++launches_;
   const double M = (double)in.B * Lw.g.out_size(in.H) * Lw.g.out_size(in.W);
-  const double K = (double)Lw.g.KH * Lw.g.KW * Lw.g.Cin;
+  double K = (double)Lw.g.KH * Lw.g.KW * Lw.g.Cin;
   const bool tc = cfg_.backend == SM_BACKEND_TENSOR && Lw.gemm_ok;
+  SMK_CHECK(in2 == nullptr || (tc && Lw.fused2), "fused second input needs the tensor-core path");
+  if (in2 != nullptr) K += (double)Lw.g2.KH * Lw.g2.KW * Lw.g2.Cin;
   Scope sc(this, Lw.conv_key, tc ? "conv_gemm" : "conv_simt", 2.0 * M * K * Lw.g.Cout,
-           4.0 * ((double)in.numel() + M * Lw.g.Cout + K * Lw.g.Cout), st);
+           4.0 * ((double)in.numel() + (in2 ? (double)in2->numel() : 0.0) + M * Lw.g.Cout * (res ? 2 : 1) +
+                  K * Lw.g.Cout), st);
   if (tc) {
     ep.alpha = Lw.alpha;
-    launch_gemm_conv(in, Lw.g, Lw.w_hi, Lw.w_lo, Lw.cout_pad, ep, exact_ ? 2 : 1, num_sms_, st);
+    GemmInput gi[2] = {{in, Lw.g, 0}, {in, Lw.g, 0}};
+    int nconv = 1;
+    const Act* ident = nullptr;
+    if (in2 != nullptr) {
+      gi[1] = {*in2, Lw.g2, Lw.col2};
+      nconv = 2;
+      ep.beta = Lw.beta2;
+    } else if (res != nullptr) {
+      if (Lw.has_diag) ident = res;                                  // residual through the MMA pipeline
+      else { ep.res_hi = res->hi; ep.res_lo = res->lo; }             // epilogue-side add
+    }
+    launch_gemm_multi(gi, nconv, ident, Lw.col_diag, Lw.w_hi, Lw.w_lo, Lw.cout_pad, Lw.w_ld, ep, exact_ ? 2 : 1,
+                      num_sms_, st);
   } else {
     ep.alpha = ones_;
+    if (res != nullptr) { ep.res_hi = res->hi; ep.res_lo = res->lo; }
     launch_ref_conv(in, Lw.g, Lw.w_ref, ep, st);
   }
 }
 
-Act Engine::conv(const Act& in, const ConvW& Lw, bool relu, const Act* res, Arena& ar, cudaStream_t st) {
+Act Engine::conv(const Act& in, const ConvW& Lw, bool relu, const Act* res, Arena& ar, cudaStream_t st,
+                 const Act* in2) {
   Act out = alloc_act(ar, in.B, Lw.g.out_size(in.H), Lw.g.out_size(in.W), Lw.g.Cout);
   Epilogue ep;
   ep.relu = relu ? 1 : 0;
   ep.out_mode = OUT_NHWC_SPLIT;
   ep.out_hi = out.hi;
   ep.out_lo = out.lo;
-  if (res != nullptr) { ep.res_hi = res->hi; ep.res_lo = res->lo; }
-  conv_into(in, Lw, ep, st);
+  conv_into(in, Lw, ep, st, res, in2);
   return out;
 }
 
@@ -554,9 +625,14 @@ Act Engine::backbone(const float* x, int B, int S, Arena& ar, bool keep, cudaStr
       const std::string P = F + names[l] + "." + std::to_string(i) + ".";
       Act t1 = conv(y, L(P + "conv1"), true, nullptr, ar, st);
       Act t2 = conv(t1, L(P + "conv2"), true, nullptr, ar, st);
-      Act res = y;
-      if (i == 0) res = conv(y, L(P + "downsample.0"), false, nullptr, ar, st);
-      y = conv(t2, L(P + "conv3"), true, &res, ar, st);
+      const ConvW& c3 = L(P + "conv3");
+      if (i == 0 && cfg_.backend == SM_BACKEND_TENSOR && c3.fused2) {
+        y = conv(t2, c3, true, nullptr, ar, st, &y);            // conv3 + downsample branch in one GEMM
+      } else {
+        Act res = y;
+        if (i == 0) res = conv(y, L(P + "downsample.0"), false, nullptr, ar, st);
+        y = conv(t2, c3, true, &res, ar, st);
+      }
     }
     if (keep) named_[std::string("p") + std::to_string(l + 1)] = y;
   }
