@@ -100,6 +100,10 @@ void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, i
                        const __half* w_lo, int cout_pad, int w_ld, const Epilogue& ep, int nsplit, int num_sms,
                        cudaStream_t st);
 
+// stem_sm100.cu : 7x7/2 stem on the tensor cores (weights [64][192] K-major, k = (r*7+s)*3+c, pow2-scaled)
+void launch_stem_tc(const float* x_nchw, int B, int S, const __half* w_hi, const __half* w_lo, const float* alpha,
+                    const float* beta, Act out, int num_sms, cudaStream_t st);
+
 // simt_kernels.cu
 void launch_ref_conv(const Act& in, const ConvGeom& g, const float* w_krsc_cout, const Epilogue& ep,
                      cudaStream_t st);

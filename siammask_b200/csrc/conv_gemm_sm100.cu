@@ -22,8 +22,8 @@
 //   acc += residual * diag(2^e) streams the residual tensor through the same TMA/MMA pipeline (one extra
 //   k-block per 64 output columns) instead of stalling the epilogue on it.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one lane),
-// warps 2..5 = epilogue.  Persistent: grid = min(tiles, SMs), static round-robin over (m_tile, n_tile).
+// Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one lane),
+// warps 2..9 = epilogue (two per TMEM lane quarter).  Persistent: grid = min(tiles, SMs), static round-robin over (m_tile, n_tile).
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -38,16 +38,17 @@ constexpr int BLOCK_K = 64;   // 64 fp16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;   // two per TMEM lane quarter, alternating 32-column chunks
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
 template <int BLOCK_N, int NSPLIT>
 struct Cfg {
   static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = NSPLIT * (A_TILE_BYTES + B_TILE_BYTES);
-  // epilogue staging: 4 warps x 2 buffers x NSPLIT planes x (32 rows x 64 B)
+  // epilogue staging: 8 warps x NSPLIT planes x (32 rows x 64 B)
   static constexpr int STG_TILE_BYTES = 32 * 64;
-  static constexpr int STG_WARP_BYTES = 2 * NSPLIT * STG_TILE_BYTES;
-  static constexpr int STG_BYTES = BLOCK_N >= 32 ? 4 * STG_WARP_BYTES : 0;
+  static constexpr int STG_WARP_BYTES = NSPLIT * STG_TILE_BYTES;
+  static constexpr int STG_BYTES = BLOCK_N >= 32 ? NUM_EPI_WARPS * STG_WARP_BYTES : 0;
   static constexpr int RAW_STAGES = (SMEM_LIMIT - 2048 - STG_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = RAW_STAGES > 6 ? 6 : RAW_STAGES;
   // 2 pipeline stages x NSPLIT accumulators (exact mode keeps the hi*hi sum and the 2^-11-sized cross terms in
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);   // one arrival per epilogue warp
+      mbar_init(&tempty_bar[a], NUM_EPI_WARPS);   // one arrival per epilogue warp
     }
     if (p.staged)
       for (int i = 0; i < NSPLIT; ++i) tma_prefetch_desc(&p.tmOut[i]);
@@ -223,18 +224,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
   } else if (warp >= 2) {
     // ===================== epilogue =====================
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;         // which of the quarter's two warps: takes every other chunk
     const Epilogue& ep = p.ep;
     const int HoWo = p.Ho * p.Wo;
     int it = 0;
     if constexpr (BLOCK_N >= 32) {
       if (p.staged) {
-        // ---- staged path: TMEM -> registers -> 64B-swizzled smem -> TMA store.  Every warp owns 32 output rows
-        // and two staging buffers, so the store of chunk k overlaps the math of chunk k+1.  (A residual, if any,
-        // has already been accumulated by the identity K-segment.)
-        uint8_t* stg = stg_base + quarter * C::STG_WARP_BYTES;
+        // ---- staged path: TMEM -> registers -> 64B-swizzled smem -> TMA store.  Two warps share each block of 32
+        // output rows and alternate 32-column chunks, each with its own staging buffer, so one warp's store and
+        // TMEM latency overlap the other's math.  (A residual, if any, was accumulated by the identity segment.)
+        uint8_t* buf = stg_base + (warp - 2) * C::STG_WARP_BYTES;
         constexpr int CHUNKS = BLOCK_N / 32;
         const int swz = (lane >> 1) & 3;                       // Swizzle<2,4,3>: 16B chunk ^= (row >> 1) & 3
-        uint32_t kchunk = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
           const int acc = it & 1;
           const uint32_t acc_phase = (it >> 1) & 1;
@@ -244,8 +245,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
           tcgen05_fence_after();
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * C::ACC_COLS;
 #pragma unroll 1
-          for (int c = 0; c < CHUNKS; ++c, ++kchunk) {
-            uint8_t* buf = stg + (kchunk & 1) * NSPLIT * C::STG_TILE_BYTES;
+          for (int c = half; c < CHUNKS; c += 2) {
             uint32_t r[32];
             tmem_ld_chunk<32>(taddr + c * 32, r);
             if constexpr (NSPLIT == 2) {
@@ -272,8 +272,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
-            // this buffer was handed to the TMA two chunks ago: wait until that store has read it
-            if (lane == 0) tma_store_wait_read<1>();
+            // the staging buffer was handed to the TMA one chunk ago: wait until that store has read it
+            if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * C::ACC_COLS;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+      for (int c0 = half * CH; c0 < BLOCK_N; c0 += 2 * CH) {
         uint32_t r[CH];
         tmem_ld_chunk<CH>(taddr + c0, r);
         if constexpr (NSPLIT == 2) {
@@ -514,6 +514,23 @@ void launch_cfg(const GemmParams& p, int num_sms, cudaStream_t st) {
 }
 
 }  // namespace
+
+// 2-D fp16 tensor map with a chosen swizzle span (32 / 64 / 128 bytes); shared with stem_sm100.cu
+CUtensorMap make_map_2d_any(const __half* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer,
+                            int swizzle_bytes) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * sizeof(__half)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = driver_api().tiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides,
+                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SMK_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed, code " + std::to_string((int)r));
+  return m;
+}
 
 bool gemm_conv_supported(const ConvGeom& g) { return g.Cin % BLOCK_K == 0 && g.Cout >= 1; }
 

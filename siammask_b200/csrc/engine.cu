@@ -135,6 +135,10 @@ class Engine {
   std::map<std::string, ConvW> layers_;
   std::vector<std::string> layer_order_;
   size_t off_deconv_w_ = 0, off_deconv_b_ = 0, off_ones_ = 0;
+  size_t off_stem_whi_ = 0, off_stem_wlo_ = 0, off_stem_alpha_ = 0;
+  __half* stem_whi_ = nullptr;
+  __half* stem_wlo_ = nullptr;
+  float* stem_alpha_ = nullptr;
   float* deconv_w_ = nullptr;
   float* deconv_b_ = nullptr;
   float* ones_ = nullptr;              // alpha for the SIMT reference path (weights unscaled)
@@ -283,6 +287,9 @@ void Engine::assign_blob_layout() {
     w.off_beta = off;  off = align_up(off + (size_t)w.cout_pad * sizeof(float));
   }
   off_ones_ = off; off = align_up(off + 4096 * sizeof(float));
+  off_stem_whi_ = off; off = align_up(off + 64 * 192 * sizeof(__half));
+  off_stem_wlo_ = off; off = align_up(off + 64 * 192 * sizeof(__half));
+  off_stem_alpha_ = off; off = align_up(off + 64 * sizeof(float));
   if (cfg_.with_mask) {
     off_deconv_w_ = off; off = align_up(off + (size_t)256 * 7200 * sizeof(float));
     off_deconv_b_ = off; off = align_up(off + 32 * sizeof(float));
@@ -318,6 +325,9 @@ Engine::Engine(const sm_config& cfg) : cfg_(cfg), exact_(cfg.precision == SM_PRE
     w.beta2 = reinterpret_cast<float*>(blob_ + w.off_beta2);
   }
   ones_ = reinterpret_cast<float*>(blob_ + off_ones_);
+  stem_whi_ = reinterpret_cast<__half*>(blob_ + off_stem_whi_);
+  stem_wlo_ = reinterpret_cast<__half*>(blob_ + off_stem_wlo_);
+  stem_alpha_ = reinterpret_cast<float*>(blob_ + off_stem_alpha_);
   if (cfg_.with_mask) {
     deconv_w_ = reinterpret_cast<float*>(blob_ + off_deconv_w_);
     deconv_b_ = reinterpret_cast<float*>(blob_ + off_deconv_b_);
@@ -510,6 +520,27 @@ void Engine::load_weights(const sm_tensor_desc* t, int n) {
   for (const auto& k : layer_order_) pack_layer(layers_[k], sd, host.data());
   float* ones = reinterpret_cast<float*>(host.data() + off_ones_);
   for (int i = 0; i < 4096; ++i) ones[i] = 1.f;
+  {
+    // tensor-core stem: [64][192] K-major, k = (r*7+s)*3 + c — exactly the row index of the folded w_ref
+    const ConvW& stem = layers_["features.features.conv1"];
+    const float* wref = reinterpret_cast<const float*>(host.data() + stem.off_wref);
+    __half* sh = reinterpret_cast<__half*>(host.data() + off_stem_whi_);
+    __half* sl = reinterpret_cast<__half*>(host.data() + off_stem_wlo_);
+    float* sa = reinterpret_cast<float*>(host.data() + off_stem_alpha_);
+    for (int n = 0; n < 64; ++n) {
+      float amax = 0.f;
+      for (int k = 0; k < 147; ++k) amax = std::max(amax, std::fabs(wref[(size_t)k * 64 + n]));
+      int e = amax > 0.f ? (int)std::floor(std::log2(16384.0 / (double)amax)) : 0;
+      e = std::max(-14, std::min(14, e));
+      sa[n] = std::ldexp(1.f, -e);
+      for (int k = 0; k < 147; ++k) {
+        const float fw = std::ldexp(wref[(size_t)k * 64 + n], e);
+        const __half h = __float2half_rn(fw);
+        sh[n * 192 + k] = h;
+        sl[n * 192 + k] = __float2half_rn(fw - __half2float(h));
+      }
+    }
+  }
   if (cfg_.with_mask) {
     // ConvTranspose2d weight (Cin=256, Cout=32, 15, 15) -> [k][(y*15+x)*32 + co]
     const float* dw = find_tensor(sd, "refine_model.deconv.weight", (size_t)256 * 32 * 225);
@@ -607,7 +638,8 @@ Act Engine::backbone(const float* x, int B, int S, Arena& ar, bool keep, cudaStr
   const ConvW& stem = L(F + "conv1");
   if (!measuring_) {
     Scope sc(this, "stem", "stem", 2.0 * B * So * So * 64 * 147, 4.0 * B * (3.0 * S * S + 64.0 * So * So), st);
-    launch_stem(x, B, S, stem.w_ref, ones_, stem.beta, p0, st);
+    if (cfg_.backend == SM_BACKEND_TENSOR) launch_stem_tc(x, B, S, stem_whi_, stem_wlo_, stem_alpha_, stem.beta, p0, num_sms_, st);
+    else launch_stem(x, B, S, stem.w_ref, ones_, stem.beta, p0, st);
     ++launches_;
   }
   const int Sp = (So + 2 - 3) / 2 + 1;
