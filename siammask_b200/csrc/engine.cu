@@ -169,6 +169,26 @@ class Engine {
   size_t total_bytes_ = 0;
   bool measuring_ = false;
 
+  // independent sub-graphs (the three correlation heads; the refine stage's v-branches) run on auxiliary
+  // streams forked from / joined back into the caller's stream with events
+  static constexpr int kAux = 3;
+  cudaStream_t aux_[kAux] = {nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> sync_events_;
+  size_t sync_next_ = 0;
+  cudaEvent_t next_sync_event() {
+    cudaEvent_t e = sync_events_[sync_next_];
+    sync_next_ = (sync_next_ + 1) % sync_events_.size();
+    return e;
+  }
+  bool concurrent() const { return !profiling_; }
+  // make `to` wait for everything enqueued on `from` so far
+  void order_after(cudaStream_t from, cudaStream_t to) {
+    if (from == to) return;
+    cudaEvent_t e = next_sync_event();
+    SMK_CUDA(cudaEventRecord(e, from));
+    SMK_CUDA(cudaStreamWaitEvent(to, e, 0));
+  }
+
   // optional per-launch CUDA-event timing (bench.py roofline): records (name, category, flops, bytes, e0, e1)
   bool profiling_ = false;
   std::vector<ProfRec> prof_;
@@ -368,6 +388,9 @@ Engine::Engine(const sm_config& cfg) : cfg_(cfg), exact_(cfg.precision == SM_PRE
   SMK_CUDA(cudaMalloc(&maps_dev_, all.size() * sizeof(int)));
   SMK_CUDA(cudaMemcpy(maps_dev_, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice));
   for (int i = 0; i < 6; ++i) maps_[pairs[i][0] * 1000 + pairs[i][1]] = maps_dev_ + offs[i];
+  for (int i = 0; i < kAux; ++i) SMK_CUDA(cudaStreamCreateWithFlags(&aux_[i], cudaStreamNonBlocking));
+  sync_events_.resize(32);
+  for (auto& e : sync_events_) SMK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
   total_bytes_ = blob_bytes_ + search_arena_.cap + templ_arena_.cap + refine_arena_.cap + 2 * kc * sizeof(__half) +
                  (B * 3 * S * S + B * 6 * A * R_ * R_ + B * 127 * 127) * sizeof(float);
@@ -386,6 +409,9 @@ Engine::~Engine() {
   cudaFree(stage_mask_);
   cudaFree(stage_pos_);
   cudaFree(maps_dev_);
+  for (int i = 0; i < kAux; ++i) if (aux_[i]) cudaStreamDestroy(aux_[i]);
+  for (auto e : sync_events_) cudaEventDestroy(e);
+  for (auto e : event_pool_) cudaEventDestroy(e);
 }
 
 size_t Engine::measure_arena(int B, int S, bool search) {
@@ -719,25 +745,31 @@ void Engine::do_track(int slot0, int B, const float* x, float* cls, float* loc, 
   const int nb = (want_feats || want_mask_head) ? 3 : 2;
   float* outs[3] = {cls, loc, mask};
   for (int br = 0; br < nb; ++br) {
+    // the branches only share their input: run them side by side (their 1x1 heads and the xcorr do not fill
+    // the GPU on their own)
+    cudaStream_t bs = (concurrent() && br > 0) ? aux_[br - 1] : st;
+    order_after(st, bs);
     const std::string P = kBranch[br];
-    Act cs = conv(xf, L(P + "conv_search.0"), true, nullptr, search_arena_, st);
+    Act cs = conv(xf, L(P + "conv_search.0"), true, nullptr, search_arena_, bs);
     Act corr = alloc_act(search_arena_, B, cs.H - 4, cs.W - 4, 256);
     const size_t off = ((size_t)br * cfg_.num_slots + slot0) * 25 * 256;
     {
       Scope sc(this, std::string(kCorrName[br]), "xcorr", 2.0 * 25 * corr.numel(),
-               4.0 * (cs.numel() + corr.numel() + (double)B * 25 * 256), st);
-      launch_xcorr_nhwc(cs, kcache_hi_ + off, exact_ ? kcache_lo_ + off : nullptr, 5, 5, corr, st);
+               4.0 * (cs.numel() + corr.numel() + (double)B * 25 * 256), bs);
+      launch_xcorr_nhwc(cs, kcache_hi_ + off, exact_ ? kcache_lo_ + off : nullptr, 5, 5, corr, bs);
       ++launches_;
     }
     named_[kCorrName[br]] = corr;
-    if (br == 2 && !want_mask_head) break;
-    Act h = conv(corr, L(P + "head.0"), true, nullptr, search_arena_, st);
-    Epilogue ep;
-    ep.relu = 0;
-    ep.out_mode = OUT_NCHW_F32;
-    ep.out_f32 = outs[br];
-    conv_into(h, L(P + "head.3"), ep, st);
+    if (!(br == 2 && !want_mask_head)) {
+      Act h = conv(corr, L(P + "head.0"), true, nullptr, search_arena_, bs);
+      Epilogue ep;
+      ep.relu = 0;
+      ep.out_mode = OUT_NCHW_F32;
+      ep.out_f32 = outs[br];
+      conv_into(h, L(P + "head.3"), ep, bs);
+    }
   }
+  for (int br = 1; br < nb; ++br) order_after((concurrent()) ? aux_[br - 1] : st, st);
   last_B_ = B;
   have_mask_feats_ = want_feats || want_mask_head;
 }
@@ -769,7 +801,37 @@ void Engine::do_refine(int B, const int32_t* pos, float* out, cudaStream_t st) {
   const Act& p1 = named_["p1"];
   const Act& p2 = named_["p2"];
   const Act& corr = named_["corr_mask"];
-  // p3 = corr_feature[:, :, dy, dx]; out = deconv(p3)
+  // The three v-branches (crop -> conv -> conv on p2 / p1 / p0) depend only on the cached pyramid: they run on
+  // auxiliary streams while the main stream walks deconv -> h2 -> post0 -> h1 -> post1 -> h0 -> post2.
+  cudaStream_t s2 = concurrent() ? aux_[0] : st, s1 = concurrent() ? aux_[1] : st, s0 = concurrent() ? aux_[2] : st;
+  order_after(st, s2);
+  order_after(st, s1);
+  order_after(st, s0);
+  // level 2 branch (15x15)
+  Act c2 = alloc_act(ar, B, 15, 15, 512);
+  {
+    Scope sc(this, "crop_p2", "refine_misc", 0, 8.0 * c2.numel(), s2);
+    launch_refine_crop(p2, pos, 1, 4, 15, c2, s2); ++launches_;
+  }
+  Act v2a = conv(c2, L(R + "v2.0"), true, nullptr, ar, s2);
+  F32T v2b = conv_f32(v2a, L(R + "v2.2"), true, ar, s2);
+  // level 1 branch (31x31)
+  Act c1 = alloc_act(ar, B, 31, 31, 256);
+  {
+    Scope sc(this, "crop_p1", "refine_misc", 0, 8.0 * c1.numel(), s1);
+    launch_refine_crop(p1, pos, 2, 8, 31, c1, s1); ++launches_;
+  }
+  Act v1a = conv(c1, L(R + "v1.0"), true, nullptr, ar, s1);
+  F32T v1b = conv_f32(v1a, L(R + "v1.2"), true, ar, s1);
+  // level 0 branch (61x61)
+  Act c0 = alloc_act(ar, B, 61, 61, 64);
+  {
+    Scope sc(this, "crop_p0", "refine_misc", 0, 8.0 * c0.numel(), s0);
+    launch_refine_crop(p0, pos, 4, 16, 61, c0, s0); ++launches_;
+  }
+  F32T v0a = conv_f32(c0, L(R + "v0.0"), true, ar, s0);
+  F32T v0b = small(v0a, nullptr, 61, L(R + "v0.2"), true, nullptr, ar, s0);
+  // main chain: p3 = corr_feature[:, :, dy, dx]; out = deconv(p3)
   float* p3 = static_cast<float*>(ar.alloc((size_t)B * 256 * sizeof(float)));
   F32T d = alloc_f32(ar, B, 15, 15, 32);
   {
@@ -777,39 +839,18 @@ void Engine::do_refine(int B, const int32_t* pos, float* out, cudaStream_t st) {
     launch_gather_corr(corr, pos, p3, st); ++launches_;
     launch_deconv(p3, deconv_w_, deconv_b_, d.p, B, 256, 7200, 32, st); ++launches_;
   }
-  // level 2 (15x15): post0(up31(h2(out) + v2(p2)))
-  Act c2 = alloc_act(ar, B, 15, 15, 512);
-  {
-    Scope sc(this, "crop_p2", "refine_misc", 0, 8.0 * c2.numel(), st);
-    launch_refine_crop(p2, pos, 1, 4, 15, c2, st); ++launches_;
-  }
-  Act v2a = conv(c2, L(R + "v2.0"), true, nullptr, ar, st);
-  F32T v2b = conv_f32(v2a, L(R + "v2.2"), true, ar, st);
   F32T h2a = small(d, nullptr, 15, L(R + "h2.0"), true, nullptr, ar, st);
   F32T h2b = small(h2a, nullptr, 15, L(R + "h2.2"), true, nullptr, ar, st);
-  F32T o0 = small(h2b, &v2b, 31, L(R + "post0"), false, nullptr, ar, st);
-  // level 1 (31x31)
-  Act c1 = alloc_act(ar, B, 31, 31, 256);
-  {
-    Scope sc(this, "crop_p1", "refine_misc", 0, 8.0 * c1.numel(), st);
-    launch_refine_crop(p1, pos, 2, 8, 31, c1, st); ++launches_;
-  }
-  Act v1a = conv(c1, L(R + "v1.0"), true, nullptr, ar, st);
-  F32T v1b = conv_f32(v1a, L(R + "v1.2"), true, ar, st);
+  order_after(s2, st);
+  F32T o0 = small(h2b, &v2b, 31, L(R + "post0"), false, nullptr, ar, st);   // post0(up31(h2 + v2))
   F32T h1a = small(o0, nullptr, 31, L(R + "h1.0"), true, nullptr, ar, st);
   F32T h1b = small(h1a, nullptr, 31, L(R + "h1.2"), true, nullptr, ar, st);
-  F32T o1 = small(h1b, &v1b, 61, L(R + "post1"), false, nullptr, ar, st);
-  // level 0 (61x61)
-  Act c0 = alloc_act(ar, B, 61, 61, 64);
-  {
-    Scope sc(this, "crop_p0", "refine_misc", 0, 8.0 * c0.numel(), st);
-    launch_refine_crop(p0, pos, 4, 16, 61, c0, st); ++launches_;
-  }
-  F32T v0a = conv_f32(c0, L(R + "v0.0"), true, ar, st);
-  F32T v0b = small(v0a, nullptr, 61, L(R + "v0.2"), true, nullptr, ar, st);
+  order_after(s1, st);
+  F32T o1 = small(h1b, &v1b, 61, L(R + "post1"), false, nullptr, ar, st);   // post1(up61(h1 + v1))
   F32T h0a = small(o1, nullptr, 61, L(R + "h0.0"), true, nullptr, ar, st);
   F32T h0b = small(h0a, nullptr, 61, L(R + "h0.2"), true, nullptr, ar, st);
-  small(h0b, &v0b, 127, L(R + "post2"), false, out, ar, st);   // (B,127,127,1) == (B,127*127)
+  order_after(s0, st);
+  small(h0b, &v0b, 127, L(R + "post2"), false, out, ar, st);                // (B,127,127,1) == (B,127*127)
 }
 
 void Engine::track_host(int slot0, int B, const float* xh, float* clsh, float* loch, const int32_t* posh, float* maskh,

@@ -193,29 +193,34 @@ __global__ void maxpool_kernel(Act in, Act out) {
 // input element is fetched KH times (rows) instead of KH*KW times; lanes are consecutive channel
 // pairs, so each warp load/store is one contiguous 128-byte line.
 template <int KH, int KW>
-__global__ void __launch_bounds__(128) xcorr_nhwc_kernel(Act x, const __half* __restrict__ k_hi,
-                                                         const __half* __restrict__ k_lo, Act out) {
+__global__ void __launch_bounds__(128, 4) xcorr_nhwc_kernel(Act x, const __half* __restrict__ k_hi,
+                                                            const __half* __restrict__ k_lo, Act out) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
   if (c >= x.C) return;
   const int i = blockIdx.y, b = blockIdx.z;
+  const __half* __restrict__ xh = x.hi;
+  const __half* __restrict__ xl = x.lo;
+  __half* __restrict__ oh = out.hi;
+  __half* __restrict__ ol = out.lo;
   float2 kk[KH][KW];
 #pragma unroll
   for (int u = 0; u < KH; ++u)
 #pragma unroll
     for (int v = 0; v < KW; ++v) kk[u][v] = split_load2(k_hi, k_lo, (((size_t)b * KH + u) * KW + v) * x.C + c);
+  const size_t row0 = ((size_t)b * x.H + i) * x.W;
   float2 win[KH][KW];
 #pragma unroll
   for (int u = 0; u < KH; ++u)
 #pragma unroll
-    for (int v = 0; v < KW - 1; ++v)
-      win[u][v + 1] = split_load2(x.hi, x.lo, (((size_t)b * x.H + i + u) * x.W + v) * x.C + c);
+    for (int v = 0; v < KW; ++v)
+      win[u][v] = split_load2(xh, xl, (row0 + (size_t)u * x.W + v) * x.C + c);
   for (int j = 0; j < out.W; ++j) {
+    // fetch the column that enters the window next iteration before doing this iteration's math
+    float2 nxt[KH];
+    const bool more = j + 1 < out.W;
 #pragma unroll
-    for (int u = 0; u < KH; ++u) {
-#pragma unroll
-      for (int v = 0; v < KW - 1; ++v) win[u][v] = win[u][v + 1];
-      win[u][KW - 1] = split_load2(x.hi, x.lo, (((size_t)b * x.H + i + u) * x.W + j + KW - 1) * x.C + c);
-    }
+    for (int u = 0; u < KH; ++u)
+      nxt[u] = more ? split_load2(xh, xl, (row0 + (size_t)u * x.W + j + KW) * x.C + c) : make_float2(0.f, 0.f);
     float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
     for (int u = 0; u < KH; ++u)
@@ -224,7 +229,13 @@ __global__ void __launch_bounds__(128) xcorr_nhwc_kernel(Act x, const __half* __
         acc.x = fmaf(win[u][v].x, kk[u][v].x, acc.x);
         acc.y = fmaf(win[u][v].y, kk[u][v].y, acc.y);
       }
-    split_store2(out.hi, out.lo, (((size_t)b * out.H + i) * out.W + j) * out.C + c, acc);
+    split_store2(oh, ol, (((size_t)b * out.H + i) * out.W + j) * out.C + c, acc);
+#pragma unroll
+    for (int u = 0; u < KH; ++u) {
+#pragma unroll
+      for (int v = 0; v < KW - 1; ++v) win[u][v] = win[u][v + 1];
+      win[u][KW - 1] = nxt[u];
+    }
   }
 }
 
@@ -395,23 +406,28 @@ __global__ void export_nchw_kernel(Act in, float* __restrict__ out) {
 // Refine-stage 3x3 pad-1 convs with 1..32 output channels on fp32 NHWC (custom.py:102-124,150-152).
 // The input is up(a (+ b)): an optional second operand (the h_i + v_i sum) and a nearest-neighbour
 // upsample (index tables computed on the host exactly as ATen does) are fused into the fetch.
-// Thread = one output pixel, all COUT channels in registers; weights [3][3][Cin][COUT] in smem.
-template <int COUT>
+// Thread = one output pixel x CPT output channels; the COUT/CPT threads of a pixel are adjacent lanes
+// (their input loads coalesce into one broadcast, their weight reads are consecutive float4s);
+// weights [3][3][Cin][COUT] live in smem.
+template <int COUT, int CPT>
 __global__ void __launch_bounds__(128) small_conv3x3_kernel(const float* __restrict__ a, const float* __restrict__ b2,
                                                             int B, int Hi, int Wi, int Ho, int Wo, int Cin,
                                                             const int* __restrict__ ymap, const int* __restrict__ xmap,
                                                             const float* __restrict__ w, const float* __restrict__ bias,
                                                             int relu, float* __restrict__ out) {
+  constexpr int G = COUT / CPT;
   extern __shared__ float sw[];   // 9*Cin*COUT weights
   for (int i = threadIdx.x; i < 9 * Cin * COUT; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
-  const size_t m = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t m = gid / G;
+  const int co0 = (int)(gid % G) * CPT;
   if (m >= (size_t)B * Ho * Wo) return;
   const int xo = m % Wo, yo = (m / Wo) % Ho;
   const int b = m / ((size_t)Wo * Ho);
-  float acc[COUT];
+  float acc[CPT];
 #pragma unroll
-  for (int j = 0; j < COUT; ++j) acc[j] = bias[j];
+  for (int j = 0; j < CPT; ++j) acc[j] = bias[co0 + j];
   for (int r = 0; r < 3; ++r) {
     const int y = yo + r - 1;
     if (y < 0 || y >= Ho) continue;
@@ -420,25 +436,46 @@ __global__ void __launch_bounds__(128) small_conv3x3_kernel(const float* __restr
       const int x = xo + s - 1;
       if (x < 0 || x >= Wo) continue;
       const size_t src = (((size_t)b * Hi + ys) * Wi + xmap[x]) * Cin;
-      const float* wt = sw + (r * 3 + s) * Cin * COUT;
+      const float* wt = sw + (r * 3 + s) * Cin * COUT + co0;
+#pragma unroll 2
       for (int c = 0; c < Cin; c += 4) {
         float4 v = *reinterpret_cast<const float4*>(a + src + c);
         if (b2 != nullptr) {
           const float4 v2 = *reinterpret_cast<const float4*>(b2 + src + c);
           v.x += v2.x; v.y += v2.y; v.z += v2.z; v.w += v2.w;
         }
+        const float vin[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < COUT; ++j) {
-          acc[j] = fmaf(v.x, wt[(c + 0) * COUT + j], acc[j]);
-          acc[j] = fmaf(v.y, wt[(c + 1) * COUT + j], acc[j]);
-          acc[j] = fmaf(v.z, wt[(c + 2) * COUT + j], acc[j]);
-          acc[j] = fmaf(v.w, wt[(c + 3) * COUT + j], acc[j]);
+        for (int q = 0; q < 4; ++q) {
+          if constexpr (CPT % 4 == 0) {
+#pragma unroll
+            for (int j = 0; j < CPT; j += 4) {
+              const float4 wv = *reinterpret_cast<const float4*>(wt + (c + q) * COUT + j);
+              acc[j + 0] = fmaf(vin[q], wv.x, acc[j + 0]);
+              acc[j + 1] = fmaf(vin[q], wv.y, acc[j + 1]);
+              acc[j + 2] = fmaf(vin[q], wv.z, acc[j + 2]);
+              acc[j + 3] = fmaf(vin[q], wv.w, acc[j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) acc[j] = fmaf(vin[q], wt[(c + q) * COUT + j], acc[j]);
+          }
         }
       }
     }
   }
+  float* dst = out + m * COUT + co0;
+  if constexpr (CPT % 4 == 0) {
 #pragma unroll
-  for (int j = 0; j < COUT; ++j) out[m * COUT + j] = relu ? fmaxf(acc[j], 0.f) : acc[j];
+    for (int j = 0; j < CPT; j += 4) {
+      float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      *reinterpret_cast<float4*>(dst + j) = o;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) dst[j] = relu ? fmaxf(acc[j], 0.f) : acc[j];
+  }
 }
 
 inline int grid_for(size_t total, int block) {
@@ -543,14 +580,15 @@ void launch_small_conv3x3_maps(const float* a, const float* b, int B, int Hi, in
                                float* out, cudaStream_t st) {
   SMK_CHECK(Cin % 4 == 0, "small conv needs Cin % 4 == 0");
   const size_t M = (size_t)B * Ho * Wo;
-  const int grid = (int)((M + 127) / 128);
   const size_t smem = (size_t)9 * Cin * Cout * sizeof(float);
-#define SMK_SC(CO)                                                                                               \
-  case CO:                                                                                                       \
-    small_conv3x3_kernel<CO><<<grid, 128, smem, st>>>(a, b, B, Hi, Wi, Ho, Wo, Cin, ymap, xmap, w, bias, relu, out); \
-    break;
+#define SMK_SC(CO, CPT)                                                                                          \
+  case CO: {                                                                                                     \
+    const size_t threads = M * (CO / CPT);                                                                       \
+    small_conv3x3_kernel<CO, CPT><<<(unsigned)((threads + 127) / 128), 128, smem, st>>>(                         \
+        a, b, B, Hi, Wi, Ho, Wo, Cin, ymap, xmap, w, bias, relu, out);                                           \
+  } break;
   switch (Cout) {
-    SMK_SC(1) SMK_SC(4) SMK_SC(16) SMK_SC(32)
+    SMK_SC(1, 1) SMK_SC(4, 4) SMK_SC(16, 4) SMK_SC(32, 8)
     default: SMK_CHECK(false, "small conv: unsupported Cout");
   }
 #undef SMK_SC
