@@ -192,49 +192,67 @@ __global__ void maxpool_kernel(Act in, Act out) {
 // Thread = (b, output row i, channel pair); it slides a KHxKW register window along j so every
 // input element is fetched KH times (rows) instead of KH*KW times; lanes are consecutive channel
 // pairs, so each warp load/store is one contiguous 128-byte line.
-template <int KH, int KW>
-__global__ void __launch_bounds__(128, 4) xcorr_nhwc_kernel(Act x, const __half* __restrict__ k_hi,
-                                                            const __half* __restrict__ k_lo, Act out) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
-  if (c >= x.C) return;
-  const int i = blockIdx.y, b = blockIdx.z;
+// Block = (sample b, chunk of XC_CH channels): the whole HxW input tile of those channels is reconstructed to
+// fp32 in shared memory once (each element is read from L2 exactly once), then every thread (channel, output
+// row) slides a KHxKW window along the row out of smem.  Lanes are consecutive channels: conflict-free LDS and
+// contiguous 64-byte stores per plane.
+template <int KH, int KW, int XC_CH>
+__global__ void __launch_bounds__(256) xcorr_nhwc_kernel(Act x, const __half* __restrict__ k_hi,
+                                                         const __half* __restrict__ k_lo, Act out) {
+  extern __shared__ float xs[];                  // [H*W][XC_CH]
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * XC_CH;
   const __half* __restrict__ xh = x.hi;
   const __half* __restrict__ xl = x.lo;
-  __half* __restrict__ oh = out.hi;
-  __half* __restrict__ ol = out.lo;
-  float2 kk[KH][KW];
+  const int npix = x.H * x.W;
+  // cooperative load: 8 channels (16 B per plane) per thread-iteration
+  for (int idx = threadIdx.x; idx < npix * (XC_CH / 8); idx += blockDim.x) {
+    const int pix = idx / (XC_CH / 8);
+    const int cc = (idx - pix * (XC_CH / 8)) * 8;
+    const size_t src = ((size_t)b * npix + pix) * x.C + c0 + cc;
+    const uint4 h = *reinterpret_cast<const uint4*>(xh + src);
+    const __half2* hh = reinterpret_cast<const __half2*>(&h);
+    float v[8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { const float2 f = __half22float2(hh[t]); v[2 * t] = f.x; v[2 * t + 1] = f.y; }
+    if (xl != nullptr) {
+      const uint4 l = *reinterpret_cast<const uint4*>(xl + src);
+      const __half2* ll = reinterpret_cast<const __half2*>(&l);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { const float2 f = __half22float2(ll[t]); v[2 * t] += f.x; v[2 * t + 1] += f.y; }
+    }
+    float4* dst = reinterpret_cast<float4*>(xs + (size_t)pix * XC_CH + cc);
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  const int lane_c = threadIdx.x % XC_CH;          // channel within the chunk
+  const int c = c0 + lane_c;
+  float kk[KH][KW];
 #pragma unroll
   for (int u = 0; u < KH; ++u)
 #pragma unroll
-    for (int v = 0; v < KW; ++v) kk[u][v] = split_load2(k_hi, k_lo, (((size_t)b * KH + u) * KW + v) * x.C + c);
-  const size_t row0 = ((size_t)b * x.H + i) * x.W;
-  float2 win[KH][KW];
-#pragma unroll
-  for (int u = 0; u < KH; ++u)
-#pragma unroll
-    for (int v = 0; v < KW; ++v)
-      win[u][v] = split_load2(xh, xl, (row0 + (size_t)u * x.W + v) * x.C + c);
-  for (int j = 0; j < out.W; ++j) {
-    // fetch the column that enters the window next iteration before doing this iteration's math
-    float2 nxt[KH];
-    const bool more = j + 1 < out.W;
-#pragma unroll
-    for (int u = 0; u < KH; ++u)
-      nxt[u] = more ? split_load2(xh, xl, (row0 + (size_t)u * x.W + j + KW) * x.C + c) : make_float2(0.f, 0.f);
-    float2 acc = make_float2(0.f, 0.f);
+    for (int v = 0; v < KW; ++v) kk[u][v] = split_load(k_hi, k_lo, (((size_t)b * KH + u) * KW + v) * x.C + c);
+  __syncthreads();
+  const int rows_per_pass = blockDim.x / XC_CH;
+  for (int i = threadIdx.x / XC_CH; i < out.H; i += rows_per_pass) {
+    float win[KH][KW];
 #pragma unroll
     for (int u = 0; u < KH; ++u)
 #pragma unroll
-      for (int v = 0; v < KW; ++v) {
-        acc.x = fmaf(win[u][v].x, kk[u][v].x, acc.x);
-        acc.y = fmaf(win[u][v].y, kk[u][v].y, acc.y);
+      for (int v = 0; v < KW - 1; ++v) win[u][v + 1] = xs[((size_t)(i + u) * x.W + v) * XC_CH + lane_c];
+    for (int j = 0; j < out.W; ++j) {
+#pragma unroll
+      for (int u = 0; u < KH; ++u) {
+#pragma unroll
+        for (int v = 0; v < KW - 1; ++v) win[u][v] = win[u][v + 1];
+        win[u][KW - 1] = xs[((size_t)(i + u) * x.W + j + KW - 1) * XC_CH + lane_c];
       }
-    split_store2(oh, ol, (((size_t)b * out.H + i) * out.W + j) * out.C + c, acc);
+      float acc = 0.f;
 #pragma unroll
-    for (int u = 0; u < KH; ++u) {
+      for (int u = 0; u < KH; ++u)
 #pragma unroll
-      for (int v = 0; v < KW - 1; ++v) win[u][v] = win[u][v + 1];
-      win[u][KW - 1] = nxt[u];
+        for (int v = 0; v < KW; ++v) acc = fmaf(win[u][v], kk[u][v], acc);
+      split_store(out.hi, out.lo, (((size_t)b * out.H + i) * out.W + j) * out.C + c, acc);
     }
   }
 }
@@ -409,72 +427,80 @@ __global__ void export_nchw_kernel(Act in, float* __restrict__ out) {
 // Thread = one output pixel x CPT output channels; the COUT/CPT threads of a pixel are adjacent lanes
 // (their input loads coalesce into one broadcast, their weight reads are consecutive float4s);
 // weights [3][3][Cin][COUT] live in smem.
-template <int COUT, int CPT>
-__global__ void __launch_bounds__(128) small_conv3x3_kernel(const float* __restrict__ a, const float* __restrict__ b2,
-                                                            int B, int Hi, int Wi, int Ho, int Wo, int Cin,
+template <int CIN, int COUT, int CPT>
+__global__ void __launch_bounds__(256) small_conv3x3_kernel(const float* __restrict__ a, const float* __restrict__ b2,
+                                                            int B, int Hi, int Wi, int Ho, int Wo,
                                                             const int* __restrict__ ymap, const int* __restrict__ xmap,
                                                             const float* __restrict__ w, const float* __restrict__ bias,
                                                             int relu, float* __restrict__ out) {
   constexpr int G = COUT / CPT;
-  extern __shared__ float sw[];   // 9*Cin*COUT weights
-  for (int i = threadIdx.x; i < 9 * Cin * COUT; i += blockDim.x) sw[i] = w[i];
+  constexpr int NW = 9 * CIN * COUT;
+  __shared__ __align__(16) float sw[NW];       // weights [3][3][CIN][COUT], staged once per persistent block
+  for (int i = threadIdx.x; i < NW; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
-  const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  const size_t m = gid / G;
-  const int co0 = (int)(gid % G) * CPT;
-  if (m >= (size_t)B * Ho * Wo) return;
-  const int xo = m % Wo, yo = (m / Wo) % Ho;
-  const int b = m / ((size_t)Wo * Ho);
-  float acc[CPT];
+  const size_t total = (size_t)B * Ho * Wo * G;
+  for (size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
+    const size_t m = gid / G;
+    const int co0 = (int)(gid % G) * CPT;
+    const int xo = m % Wo, yo = (m / Wo) % Ho;
+    const int b = m / ((size_t)Wo * Ho);
+    float acc[CPT];
 #pragma unroll
-  for (int j = 0; j < CPT; ++j) acc[j] = bias[co0 + j];
-  for (int r = 0; r < 3; ++r) {
-    const int y = yo + r - 1;
-    if (y < 0 || y >= Ho) continue;
-    const int ys = ymap[y];
-    for (int s = 0; s < 3; ++s) {
-      const int x = xo + s - 1;
-      if (x < 0 || x >= Wo) continue;
-      const size_t src = (((size_t)b * Hi + ys) * Wi + xmap[x]) * Cin;
-      const float* wt = sw + (r * 3 + s) * Cin * COUT + co0;
-#pragma unroll 2
-      for (int c = 0; c < Cin; c += 4) {
-        float4 v = *reinterpret_cast<const float4*>(a + src + c);
-        if (b2 != nullptr) {
-          const float4 v2 = *reinterpret_cast<const float4*>(b2 + src + c);
-          v.x += v2.x; v.y += v2.y; v.z += v2.z; v.w += v2.w;
+    for (int j = 0; j < CPT; ++j) acc[j] = bias[co0 + j];
+#pragma unroll 1
+    for (int r = 0; r < 3; ++r) {
+      const int y = yo + r - 1;
+      if (y < 0 || y >= Ho) continue;
+      const int ys = ymap[y];
+#pragma unroll 1
+      for (int s = 0; s < 3; ++s) {
+        const int x = xo + s - 1;
+        if (x < 0 || x >= Wo) continue;
+        const size_t src = (((size_t)b * Hi + ys) * Wi + xmap[x]) * CIN;
+        float vin[CIN];
+#pragma unroll
+        for (int c = 0; c < CIN; c += 4) {       // all loads of the tap are issued before any math
+          const float4 v = *reinterpret_cast<const float4*>(a + src + c);
+          vin[c] = v.x; vin[c + 1] = v.y; vin[c + 2] = v.z; vin[c + 3] = v.w;
         }
-        const float vin[4] = {v.x, v.y, v.z, v.w};
+        if (b2 != nullptr) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+          for (int c = 0; c < CIN; c += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(b2 + src + c);
+            vin[c] += v.x; vin[c + 1] += v.y; vin[c + 2] += v.z; vin[c + 3] += v.w;
+          }
+        }
+        const float* wt = sw + (r * 3 + s) * CIN * COUT + co0;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
           if constexpr (CPT % 4 == 0) {
 #pragma unroll
             for (int j = 0; j < CPT; j += 4) {
-              const float4 wv = *reinterpret_cast<const float4*>(wt + (c + q) * COUT + j);
-              acc[j + 0] = fmaf(vin[q], wv.x, acc[j + 0]);
-              acc[j + 1] = fmaf(vin[q], wv.y, acc[j + 1]);
-              acc[j + 2] = fmaf(vin[q], wv.z, acc[j + 2]);
-              acc[j + 3] = fmaf(vin[q], wv.w, acc[j + 3]);
+              const float4 wv = *reinterpret_cast<const float4*>(wt + c * COUT + j);
+              acc[j + 0] = fmaf(vin[c], wv.x, acc[j + 0]);
+              acc[j + 1] = fmaf(vin[c], wv.y, acc[j + 1]);
+              acc[j + 2] = fmaf(vin[c], wv.z, acc[j + 2]);
+              acc[j + 3] = fmaf(vin[c], wv.w, acc[j + 3]);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) acc[j] = fmaf(vin[q], wt[(c + q) * COUT + j], acc[j]);
+            for (int j = 0; j < CPT; ++j) acc[j] = fmaf(vin[c], wt[c * COUT + j], acc[j]);
           }
         }
       }
     }
-  }
-  float* dst = out + m * COUT + co0;
-  if constexpr (CPT % 4 == 0) {
+    float* dst = out + m * COUT + co0;
+    if constexpr (CPT % 4 == 0) {
 #pragma unroll
-    for (int j = 0; j < CPT; j += 4) {
-      float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-      *reinterpret_cast<float4*>(dst + j) = o;
+      for (int j = 0; j < CPT; j += 4) {
+        float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        *reinterpret_cast<float4*>(dst + j) = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) dst[j] = relu ? fmaxf(acc[j], 0.f) : acc[j];
     }
-  } else {
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) dst[j] = relu ? fmaxf(acc[j], 0.f) : acc[j];
   }
 }
 
@@ -511,8 +537,26 @@ void launch_maxpool3s2(const Act& in, Act out, cudaStream_t st) {
 void launch_xcorr_nhwc(const Act& x, const __half* k_hi, const __half* k_lo, int kh, int kw, Act out, cudaStream_t st) {
   SMK_CHECK(kh == 5 && kw == 5, "engine xcorr is specialised for the 5x5 template kernel");
   SMK_CHECK(out.H == x.H - kh + 1 && out.W == x.W - kw + 1 && out.C == x.C && x.C % 2 == 0, "xcorr shapes");
-  dim3 grid((x.C / 2 + 127) / 128, out.H, x.B);
-  xcorr_nhwc_kernel<5, 5><<<grid, 128, 0, st>>>(x, k_hi, k_lo, out);
+  SMK_CHECK(x.C % 32 == 0, "xcorr channel chunking");
+  // 32 channels per block when the HxW tile fits (29x29 @255: 105 KB), else 16 (45x45 @383: 127 KB)
+  const size_t smem32 = (size_t)x.H * x.W * 32 * sizeof(float);
+  if (smem32 <= 110 * 1024) {
+    static size_t attr = 0;
+    if (smem32 > attr) {
+      SMK_CUDA(cudaFuncSetAttribute(xcorr_nhwc_kernel<5, 5, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+      attr = smem32;
+    }
+    xcorr_nhwc_kernel<5, 5, 32><<<dim3(x.C / 32, x.B), 256, smem32, st>>>(x, k_hi, k_lo, out);
+  } else {
+    const size_t smem16 = smem32 / 2;
+    SMK_CHECK(smem16 <= 220 * 1024, "xcorr input tile does not fit shared memory");
+    static size_t attr = 0;
+    if (smem16 > attr) {
+      SMK_CUDA(cudaFuncSetAttribute(xcorr_nhwc_kernel<5, 5, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+      attr = smem16;
+    }
+    xcorr_nhwc_kernel<5, 5, 16><<<dim3(x.C / 16, x.B), 256, smem16, st>>>(x, k_hi, k_lo, out);
+  }
   SMK_CUDA(cudaGetLastError());
 }
 
@@ -578,19 +622,19 @@ std::vector<int> nearest_index_table(int out_size, int in_size) {
 void launch_small_conv3x3_maps(const float* a, const float* b, int B, int Hi, int Wi, int Ho, int Wo, int Cin, int Cout,
                                const int* ymap, const int* xmap, const float* w, const float* bias, int relu,
                                float* out, cudaStream_t st) {
-  SMK_CHECK(Cin % 4 == 0, "small conv needs Cin % 4 == 0");
   const size_t M = (size_t)B * Ho * Wo;
-  const size_t smem = (size_t)9 * Cin * Cout * sizeof(float);
-#define SMK_SC(CO, CPT)                                                                                          \
-  case CO: {                                                                                                     \
+#define SMK_SC(CI, CO, CPT)                                                                                      \
+  if (Cin == CI && Cout == CO) {                                                                                 \
     const size_t threads = M * (CO / CPT);                                                                       \
-    small_conv3x3_kernel<CO, CPT><<<(unsigned)((threads + 127) / 128), 128, smem, st>>>(                         \
-        a, b, B, Hi, Wi, Ho, Wo, Cin, ymap, xmap, w, bias, relu, out);                                           \
-  } break;
-  switch (Cout) {
-    SMK_SC(1, 1) SMK_SC(4, 4) SMK_SC(16, 4) SMK_SC(32, 8)
-    default: SMK_CHECK(false, "small conv: unsupported Cout");
+    size_t blocks = (threads + 255) / 256;                                                                       \
+    if (blocks > 148 * 6) blocks = 148 * 6;                                                                      \
+    small_conv3x3_kernel<CI, CO, CPT><<<(unsigned)blocks, 256, 0, st>>>(a, b, B, Hi, Wi, Ho, Wo, ymap, xmap, w,  \
+                                                                          bias, relu, out);                      \
+    launched = true;                                                                                             \
   }
+  bool launched = false;
+  SMK_SC(32, 32, 8) SMK_SC(32, 16, 4) SMK_SC(16, 16, 4) SMK_SC(16, 4, 4) SMK_SC(4, 4, 4) SMK_SC(4, 1, 1)
+  SMK_CHECK(launched, "small conv: unsupported (Cin, Cout)");
 #undef SMK_SC
   SMK_CUDA(cudaGetLastError());
 }
