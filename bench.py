@@ -185,20 +185,22 @@ def run_gpu(args, rank, local_rank, world):
     import torch.distributed as dist
     import siammask_b200 as smb
     from siammask_b200 import _lib
+    from siammask_b200.parallel import broadcast_weights, max_over_ranks, shard_streams
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B, S = args.batch, args.search
+    S = args.search
+    # weak scaling: args.batch streams per GPU; this rank owns a contiguous block of the global stream ids
+    B = len(shard_streams(args.batch * world, world, rank))
     R = (S - 127) // 8 + 9
     m = smb.Custom(anchors=smb.DEFAULT_ANCHORS, search_size=S, max_batch=B, num_slots=B, precision=args.precision)
     if rank == 0:
         m.load_state_dict(smb.synthetic_state_dict(0))
     m.eval().to(dev)
     if world > 1:                       # the one collective of the whole job: weights, once, at init
-        blob = m.weight_blob()
-        dist.broadcast(blob, src=0)
+        broadcast_weights(m.weight_blob(), src=0)
         torch.cuda.synchronize()
         if rank != 0:
             m.adopt_weights()
@@ -227,10 +229,7 @@ def run_gpu(args, rank, local_rank, world):
             fn(i)
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return max_over_ranks(e0.elapsed_time(e1), device=dev)
 
     for i in range(max(args.warmup, 3)):
         step(i)
@@ -264,10 +263,8 @@ def run_gpu(args, rank, local_rank, world):
     t0 = time.perf_counter()
     for i in range(args.steps):
         host_step(i)          # synchronises the stream itself (results are in host memory on return)
-    dt = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_fps = world * B * args.steps / float(dt.item())
+    dt = max_over_ranks(time.perf_counter() - t0, device=dev)
+    e2e_fps = world * B * args.steps / dt
     h2d = xh[0].numel() * 4 + posh.numel() * 4
     d2h = (clsh.numel() + loch.numel() + maskh.numel()) * 4
 
