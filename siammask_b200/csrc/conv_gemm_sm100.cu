@@ -34,16 +34,19 @@ namespace smk {
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;   // 64 fp16 = one 128-byte swizzle row
+constexpr int CIN_GRAIN = 64;  // convs need Cin % 64 == 0 (both k-block widths divide it)
 constexpr int UMMA_K = 16;
-constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int NUM_EPI_WARPS = 8;   // two per TMEM lane quarter, alternating 32-column chunks
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
-template <int BLOCK_N, int NSPLIT>
+// BK = k-block width in fp16 elements: 64 (128-byte swizzled rows) or 32 (64-byte rows, finer pipeline stages)
+template <int BLOCK_N, int NSPLIT, int BK>
 struct Cfg {
-  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int BLOCK_K = BK;
+  static constexpr int SWIZZLE = BK * 2;
+  static constexpr int A_TILE_BYTES = BLOCK_M * BK * 2;
+  static constexpr int B_TILE_BYTES = BLOCK_N * BK * 2;
   static constexpr int STAGE_BYTES = NSPLIT * (A_TILE_BYTES + B_TILE_BYTES);
   // epilogue staging: 8 warps x NSPLIT planes x (32 rows x 64 B)
   static constexpr int STG_TILE_BYTES = 32 * 64;
@@ -55,9 +58,12 @@ struct Cfg {
   // separate TMEM accumulators: the tensor pipe truncates on every accumulate, so feeding small terms into the
   // large running sum — or tripling the number of adds into it — costs accuracy; they are summed in the epilogue)
   static constexpr int ACC_COLS = NSPLIT * BLOCK_N;
-  static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
-                                   : (2 * ACC_COLS <= 256) ? 256 : 512;
-  static_assert(2 * ACC_COLS <= 512, "TMEM capacity");
+  // two accumulator stages (epilogue of tile i overlaps the main loop of tile i+1) when TMEM allows, else one
+  static constexpr int ACC_STAGES = 2 * ACC_COLS <= 512 ? 2 : 1;
+  static constexpr int ACC_TOTAL = ACC_STAGES * ACC_COLS;
+  static constexpr int TMEM_COLS = (ACC_TOTAL <= 32) ? 32 : (ACC_TOTAL <= 64) ? 64 : (ACC_TOTAL <= 128) ? 128
+                                   : (ACC_TOTAL <= 256) ? 256 : 512;
+  static_assert(ACC_TOTAL <= 512, "TMEM capacity");
   static constexpr int CH = BLOCK_N < 32 ? 16 : 32;   // epilogue column chunk
   // one CTA per SM: keep the request above half of the SM's shared memory
   static constexpr int SMEM_BYTES_RAW = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -73,11 +79,13 @@ __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CH])
   else tmem_ld_32x32b_x16(taddr, r);
 }
 
-template <int BLOCK_N, int NSPLIT>
+template <int BLOCK_N, int NSPLIT, int BK>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg<BLOCK_N, NSPLIT>;
+  using C = Cfg<BLOCK_N, NSPLIT, BK>;
   constexpr int STAGES = C::STAGES;
   constexpr int CH = C::CH;
+  constexpr int BLOCK_K = BK;
+  constexpr int A_TILE_BYTES = C::A_TILE_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -181,8 +189,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = it % C::ACC_STAGES;
+      const uint32_t acc_phase = (it / C::ACC_STAGES) & 1;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * C::ACC_COLS;
@@ -201,16 +209,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint32_t koff = k * UMMA_K * 2;   // bytes along K inside the 128B swizzle row
-            const uint64_t da_hi = umma_desc_kmajor_sw128(a_hi + koff);
-            const uint64_t db_hi = umma_desc_kmajor_sw128(b_hi + koff);
+            const uint64_t da_hi = umma_desc_kmajor<C::SWIZZLE>(a_hi + koff);
+            const uint64_t db_hi = umma_desc_kmajor<C::SWIZZLE>(b_hi + koff);
             umma_f16(tmem_d, da_hi, db_hi, idesc, acc_main);
             acc_main = 1;
             if constexpr (NSPLIT == 2) {
-              const uint64_t da_lo = umma_desc_kmajor_sw128(a_hi + A_TILE_BYTES + koff);
+              const uint64_t da_lo = umma_desc_kmajor<C::SWIZZLE>(a_hi + A_TILE_BYTES + koff);
               umma_f16(tmem_d + BLOCK_N, da_lo, db_hi, idesc, acc_lo);
               acc_lo = 1;
               if (!ident) {
-                const uint64_t db_lo = umma_desc_kmajor_sw128(b_hi + C::B_TILE_BYTES + koff);
+                const uint64_t db_lo = umma_desc_kmajor<C::SWIZZLE>(b_hi + C::B_TILE_BYTES + koff);
                 umma_f16(tmem_d + BLOCK_N, da_hi, db_lo, idesc, 1u);
               }
             }
@@ -237,8 +245,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
         constexpr int CHUNKS = BLOCK_N / 32;
         const int swz = (lane >> 1) & 3;                       // Swizzle<2,4,3>: 16B chunk ^= (row >> 1) & 3
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-          const int acc = it & 1;
-          const uint32_t acc_phase = (it >> 1) & 1;
+          const int acc = it % C::ACC_STAGES;
+          const uint32_t acc_phase = (it / C::ACC_STAGES) & 1;
           const int m0 = (tile / p.n_tiles) * BLOCK_M + quarter * 32;
           const int n0 = (tile % p.n_tiles) * BLOCK_N;
           mbar_wait(&tfull_bar[acc], acc_phase);
@@ -307,8 +315,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
       }
     }
     for (int tile = blockIdx.x; it >= 0 && tile < num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = it % C::ACC_STAGES;
+      const uint32_t acc_phase = (it / C::ACC_STAGES) & 1;
       const int m0 = (tile / p.n_tiles) * BLOCK_M;
       const int n0 = (tile % p.n_tiles) * BLOCK_N;
       const int m = m0 + quarter * 32 + lane;
@@ -457,8 +465,10 @@ CUtensorMap make_map_2d(const __half* base, uint64_t inner, uint64_t outer, uint
   cuuint64_t strides[1] = {inner * sizeof(__half)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
+  // operand tiles: the swizzle span equals the k-block row (64 fp16 -> 128 B, 32 fp16 -> 64 B)
+  const CUtensorMapSwizzle sw = box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = driver_api().tiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides,
-                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SMK_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed, code " + std::to_string((int)r));
   return m;
@@ -477,7 +487,7 @@ CUtensorMap make_map_epilogue(const __half* base, uint64_t cout, uint64_t m) {
   return t;
 }
 
-CUtensorMap make_map_im2col(const __half* base, const Act& in, const ConvGeom& g) {
+CUtensorMap make_map_im2col(const __half* base, const Act& in, const ConvGeom& g, int bk) {
   CUtensorMap m;
   cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.B};
   cuuint64_t strides[3] = {(cuuint64_t)in.C * 2, (cuuint64_t)in.W * in.C * 2, (cuuint64_t)in.H * in.W * in.C * 2};
@@ -488,7 +498,8 @@ CUtensorMap make_map_im2col(const __half* base, const Act& in, const ConvGeom& g
   cuuint32_t estr[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
   const DriverApi& api = driver_api();
   CUresult r = api.im2col(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), dims, strides, lower,
-                          upper, BLOCK_K, BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          upper, bk, BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SMK_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed, code " + std::to_string((int)r));
   // Same small-tensor descriptor fix-up CuTe applies for drivers <= 13.1
@@ -498,10 +509,10 @@ CUtensorMap make_map_im2col(const __half* base, const Act& in, const ConvGeom& g
   return m;
 }
 
-template <int BLOCK_N, int NSPLIT>
+template <int BLOCK_N, int NSPLIT, int BK = 64>
 void launch_cfg(const GemmParams& p, int num_sms, cudaStream_t st) {
-  using C = Cfg<BLOCK_N, NSPLIT>;
-  auto kern = conv_gemm_kernel<BLOCK_N, NSPLIT>;
+  using C = Cfg<BLOCK_N, NSPLIT, BK>;
+  auto kern = conv_gemm_kernel<BLOCK_N, NSPLIT, BK>;
   static bool attr_set = false;
   if (!attr_set) {
     SMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -532,7 +543,7 @@ CUtensorMap make_map_2d_any(const __half* base, uint64_t inner, uint64_t outer, 
   return m;
 }
 
-bool gemm_conv_supported(const ConvGeom& g) { return g.Cin % BLOCK_K == 0 && g.Cout >= 1; }
+bool gemm_conv_supported(const ConvGeom& g) { return g.Cin % CIN_GRAIN == 0 && g.Cout >= 1; }
 
 int gemm_cout_pad(int cout) {
   if (cout <= 16) return 16;
@@ -562,7 +573,12 @@ void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, i
   p.Cout = g0.Cout;
   p.Ho = Ho;
   p.Wo = Wo;
+  // Tile choice: 128 x 128 (exact: two TMEM accumulators per tile, double buffered) or 128 x 256 (fast).
+  // A 128 x 256 exact tile (32-wide k-blocks, single accumulator stage: conv_gemm_kernel<256, 2, 32>) was measured on
+  // B200 and is NOT faster (layer3.0 fused conv 1.33 vs 1.36 ms, layer3 conv2 0.203 vs 0.183 ms): both shapes sit
+  // at the ~65 % tensor-pipe duty cycle that cuBLAS itself sustains on this part (MEASURED_PEAKS.json).
   const int block_n = cout_pad < 256 ? cout_pad : (nsplit == 2 ? 128 : 256);
+  const int bk = 64;
   SMK_CHECK(cout_pad % block_n == 0, "cout_pad must be a multiple of the N tile");
   if (ep.out_mode != OUT_NCHW_F32) SMK_CHECK(g0.Cout == cout_pad, "NHWC outputs need Cout to match the padded tile width");
   p.n_tiles = cout_pad / block_n;
@@ -577,7 +593,7 @@ void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, i
     SMK_CHECK(nsplit == 1 || (in.lo != nullptr && w_lo != nullptr), "exact mode needs lo planes");
     GemmSegment& sg = p.seg[p.nseg++];
     sg.kind = 0;
-    sg.cblks = g.Cin / BLOCK_K;
+    sg.cblks = g.Cin / bk;
     sg.num_kb = g.KH * g.KW * sg.cblks;
     sg.KW = g.KW;
     sg.stride = g.stride;
@@ -585,35 +601,35 @@ void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, i
     sg.dil = g.dil;
     sg.mode = (g.KH == 1 && g.KW == 1 && g.stride == 1 && g.pad == 0) ? 0 : 1;
     sg.b_col0 = convs[i].w_col0;
-    SMK_CHECK(sg.b_col0 % BLOCK_K == 0 && sg.b_col0 + g.KH * g.KW * g.Cin <= w_ld, "weight column range");
+    SMK_CHECK(sg.b_col0 % 64 == 0 && sg.b_col0 + g.KH * g.KW * g.Cin <= w_ld, "weight column range");
     for (int s = 0; s < nsplit; ++s) {
       const __half* a = s == 0 ? in.hi : in.lo;
-      sg.tmA[s] = sg.mode == 0 ? make_map_2d(a, g.Cin, (uint64_t)in.M(), BLOCK_K, BLOCK_M) : make_map_im2col(a, in, g);
+      sg.tmA[s] = sg.mode == 0 ? make_map_2d(a, g.Cin, (uint64_t)in.M(), bk, BLOCK_M) : make_map_im2col(a, in, g, bk);
     }
     if (nsplit == 1) sg.tmA[1] = sg.tmA[0];
   }
   bool ident = false;
   if (residual != nullptr) {
     // the residual rides the tensor pipe: needs the diag(2^e) block in the weights and 64-wide column blocks
-    SMK_CHECK(res_col0 >= 0 && res_col0 % BLOCK_K == 0 && res_col0 + g0.Cout <= w_ld && block_n % BLOCK_K == 0,
+    SMK_CHECK(res_col0 >= 0 && res_col0 % 64 == 0 && res_col0 + g0.Cout <= w_ld && block_n % 64 == 0,
               "identity segment needs a diagonal block in the packed weights");
     SMK_CHECK(residual->C == g0.Cout && residual->M() == p.M, "residual shape");
     SMK_CHECK(nsplit == 1 || residual->lo != nullptr, "exact mode residual needs both planes");
     GemmSegment& sg = p.seg[p.nseg++];
     sg.kind = 1;
     sg.mode = 0;
-    sg.num_kb = block_n / BLOCK_K;
+    sg.num_kb = block_n / bk;
     sg.cblks = sg.KW = sg.stride = sg.dil = 1;
     sg.pad = 0;
     sg.b_col0 = res_col0;
     for (int s = 0; s < nsplit; ++s)
-      sg.tmA[s] = make_map_2d(s == 0 ? residual->hi : residual->lo, g0.Cout, (uint64_t)p.M, BLOCK_K, BLOCK_M);
+      sg.tmA[s] = make_map_2d(s == 0 ? residual->hi : residual->lo, g0.Cout, (uint64_t)p.M, bk, BLOCK_M);
     if (nsplit == 1) sg.tmA[1] = sg.tmA[0];
     ident = true;
     ep.res_hi = ep.res_lo = nullptr;       // accumulated by the MMA, not by the epilogue
   }
   if (p.nseg == 1) p.seg[1] = p.seg[0];
-  for (int s = 0; s < nsplit; ++s) p.tmB[s] = make_map_2d(s == 0 ? w_hi : w_lo, (uint64_t)w_ld, cout_pad, BLOCK_K, block_n);
+  for (int s = 0; s < nsplit; ++s) p.tmB[s] = make_map_2d(s == 0 ? w_hi : w_lo, (uint64_t)w_ld, cout_pad, bk, block_n);
   if (nsplit == 1) p.tmB[1] = p.tmB[0];
   // NHWC split outputs go through smem + TMA stores; an epilogue-side residual (no diagonal block) needs the
   // direct path
@@ -639,7 +655,7 @@ void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, i
     SMK_DISPATCH(64)
     SMK_DISPATCH(128)
     case 256:
-      SMK_CHECK(nsplit == 1, "exact mode uses N tiles <= 128 (two TMEM accumulators per tile)");
+      SMK_CHECK(nsplit == 1, "exact mode uses N tiles <= 128");
       launch_cfg<256, 1>(p, num_sms, st);
       break;
     default: SMK_CHECK(false, "unsupported N tile");

@@ -247,11 +247,16 @@ __global__ void __launch_bounds__(256) xcorr_nhwc_kernel(Act x, const __half* __
         for (int v = 0; v < KW - 1; ++v) win[u][v] = win[u][v + 1];
         win[u][KW - 1] = xs[((size_t)(i + u) * x.W + j + KW - 1) * XC_CH + lane_c];
       }
-      float acc = 0.f;
+      float part[KH];                      // one partial sum per kernel row: KH independent FMA chains
 #pragma unroll
-      for (int u = 0; u < KH; ++u)
+      for (int u = 0; u < KH; ++u) {
+        part[u] = win[u][0] * kk[u][0];
 #pragma unroll
-        for (int v = 0; v < KW; ++v) acc = fmaf(win[u][v], kk[u][v], acc);
+        for (int v = 1; v < KW; ++v) part[u] = fmaf(win[u][v], kk[u][v], part[u]);
+      }
+      float acc = part[0];
+#pragma unroll
+      for (int u = 1; u < KH; ++u) acc += part[u];
       split_store(out.hi, out.lo, (((size_t)b * out.H + i) * out.W + j) * out.C + c, acc);
     }
   }
