@@ -19,6 +19,8 @@ from __future__ import annotations
 
 import argparse
 import json
+
+import numpy as np
 import os
 import statistics
 import subprocess
@@ -43,29 +45,43 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md).  The process is
+    started (and its first sample awaited) before the warm-up, so its start-up cost never lands inside the timed
+    region; a reader thread time-stamps every sample and `stop()` keeps those inside [t0, t1]."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
     NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, uuid):
-        self.proc = None
+        import threading
+        self.proc, self.lines = None, []
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", uuid, f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
-            pass
+            return
+        self.first = threading.Event()
 
-    def stop(self):
+        def reader():
+            for line in self.proc.stdout:
+                self.lines.append((time.perf_counter(), line))
+                self.first.set()
+        self.thread = threading.Thread(target=reader, daemon=True)
+        self.thread.start()
+        self.first.wait(5.0)
+
+    def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.06)
         self.proc.terminate()
-        out, _ = self.proc.communicate(timeout=10)
+        self.thread.join(5.0)
         sm, mx, pw, reasons = [], [], [], set()
-        for line in out.splitlines():
+        for ts, line in self.lines:
+            if not (t0 <= ts <= t1 + 0.03):
+                continue
             f = [t.strip() for t in line.split(",")]
             if len(f) < 7:
                 continue
@@ -77,11 +93,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # samples under load = upper half of the power readings
-        cut = statistics.median(pw)
-        loaded = [s for s, p in zip(sm, pw) if p >= cut] or sm
-        return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples inside the timed region"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
@@ -128,7 +141,7 @@ def run_reference(args, rank):
 def workload_config(args, batch_per_gpu, world):
     return {"workload": f"SiamMask-sharp config_davis, template 127 / search {args.search}, response "
                         f"{(args.search - 127) // 8 + 9}x{(args.search - 127) // 8 + 9}: track_mask (incl. 256->3969 "
-                        f"mask head) + track_refine, {batch_per_gpu} paired streams per GPU, templates cached per slot",
+                        f"mask head) + on-device score/box selection + track_refine at the selected position, {batch_per_gpu} paired streams per GPU, templates cached per slot",
             "global_batch": batch_per_gpu * world, "batch_per_gpu": batch_per_gpu, "search": args.search,
             "parallelism": f"streams sharded over {world} GPU(s), one NCCL weight broadcast at init, "
                            "no per-frame collective",
@@ -208,12 +221,20 @@ def run_gpu(args, rank, local_rank, world):
     z = torch.rand(B, 3, 127, 127, device=dev, generator=gen) * 255
     xs = [torch.rand(B, 3, S, S, device=dev, generator=gen) * 255 for _ in range(4)]
     pos = torch.randint(0, R, (B, 2), device=dev, generator=gen, dtype=torch.int32)
+    # what siamese_init prepares per stream (tools/test.py:142-161): anchors, cosine window, target size in the crop
+    from siammask_b200 import tracker
+    anchors_dev = torch.from_numpy(tracker.generate_anchor(smb.DEFAULT_ANCHORS, R)).to(dev)
+    window_dev = torch.from_numpy(np.tile(np.outer(np.hanning(R), np.hanning(R)).flatten(), 5).astype(np.float32)).to(dev)
+    tsz_dev = torch.rand(B, 2, device=dev, generator=gen) * 60 + 30
     m.template(z)
 
     def step(i, mask_head=True):
-        out = m.track_mask(xs[i % 4], mask_head=mask_head)
-        ref = m.track_refine(pos)
-        return out, ref
+        # the full per-frame path of siamese_track (tools/test.py:201-261) without leaving the device:
+        # track_mask -> score/box post-processing + argmax -> track_refine at the selected position
+        cls, loc, mask = m.track_mask(xs[i % 4], mask_head=mask_head)
+        best, sel_pos, rec = m.select(cls, loc, anchors_dev, window_dev, tsz_dev, 0.04, 0.4)
+        ref = m.track_refine(sel_pos)
+        return (cls, loc, mask, rec), ref
 
     def barrier():
         torch.cuda.synchronize()
@@ -231,13 +252,15 @@ def run_gpu(args, rank, local_rank, world):
         barrier()
         return max_over_ranks(e0.elapsed_time(e1), device=dev)
 
+    sampler = ClockSampler("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
     for i in range(max(args.warmup, 3)):
         step(i)
-    sampler = ClockSampler("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
     l0 = m.launch_count
+    t_start = time.perf_counter()
     ms = timed(step, args.steps)
+    t_end = time.perf_counter()
     launches = m.launch_count - l0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_start, t_end) if sampler else None
     fps = world * B * args.steps / (ms * 1e-3)
     ms_skip = timed(lambda i: step(i, mask_head=False), args.steps)
     fps_skip = world * B * args.steps / (ms_skip * 1e-3)

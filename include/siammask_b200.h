@@ -81,6 +81,16 @@ int sm_track(sm_engine* e, int32_t slot0, int32_t B, const float* x_nchw, float*
  * sm_track(..., SM_TRACK_MASK_FEATURES) with the same B. */
 int sm_refine(sm_engine* e, int32_t B, const int32_t* pos, float* out, void* stream);
 
+/* Score / box post-processing + argmax of siamese_track — tools/test.py:205-254 — on the device, so that
+ * sm_track -> sm_select -> sm_refine needs no host round trip.  All pointers are device pointers:
+ * cls/loc as returned by sm_track; anchors f32 [A*R*R][4] = (cx,cy,w,h) in generate_anchor order (tools/test.py:113-129);
+ * window f32 [A*R*R] (tiled hanning, :157-161); target_sz_in_crop f32 [B][2] = target_sz * scale_x (:226).
+ * Outputs: best_idx int32 [B] (np.argmax of pscore, :237), pos int32 [B][2] = (delta_y, delta_x) (:253-254),
+ * records f32 [B][8] = decoded box cx,cy,w,h of the winner in crop units (:209-212), score, penalty, pscore, 0. */
+int sm_select(sm_engine* e, int32_t B, const float* cls, const float* loc, const float* anchors, const float* window,
+              const float* target_sz_in_crop, double penalty_k, double window_influence, int32_t* best_idx, int32_t* pos,
+              float* records, void* stream);
+
 /* Whole step through HOST buffers (pinned recommended): H2D of x, track(+mask features), optional refine,
  * D2H of cls / loc / refine logits, then stream synchronise.  mask_out_host may be NULL (no refine). */
 int sm_track_host(sm_engine* e, int32_t slot0, int32_t B, const float* x_host, float* cls_host, float* loc_host,

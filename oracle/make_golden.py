@@ -33,6 +33,49 @@ def sub(t, step):
     return t.flatten()[::step].numpy().copy()
 
 
+def reference_loop_functions():
+    """Import siamese_init / siamese_track from the UNMODIFIED tools/test.py with the shims SURVEY §8c lists
+    (pyvotkit stub, numpy-2 aliases, cv2 version probe) — nothing in /root/reference is touched."""
+    import types
+    import cv2
+    stub = types.ModuleType("utils.pyvotkit.region")
+    stub.vot_overlap = lambda *a, **k: 0.0
+    stub.vot_float2str = lambda *a, **k: ""
+    sys.modules.setdefault("utils.pyvotkit.region", stub)
+    pk = types.ModuleType("utils.pyvotkit")
+    pk.__path__ = []
+    sys.modules.setdefault("utils.pyvotkit", pk)
+    for name, val in (("float", float), ("int", int), ("int0", np.intp)):
+        if not hasattr(np, name):
+            setattr(np, name, val)
+    cv2.__version__ = "4.5.0"          # tools/test.py:285 probes __version__[-5]
+    sys.path[:0] = [REF, os.path.join(REF, "experiments", "siammask_sharp")]
+    from tools.test import siamese_init, siamese_track  # noqa
+    return siamese_init, siamese_track
+
+
+def tracker_loop_golden(sd):
+    """The reference's own tracker loop (tools/test.py:132-315) driven by the oracle network on synthetic frames."""
+    from oracle.siammask_oracle import Oracle
+    from oracle.synthetic_video import make_frames
+    siamese_init, siamese_track = reference_loop_functions()
+    frames, boxes = make_frames()
+    x, y, w, h = boxes[0]
+    hp = {"instance_size": 255, "base_size": 8, "out_size": 127, "seg_thr": 0.35, "penalty_k": 0.04,
+          "window_influence": 0.4, "lr": 1.0}                      # config_davis.json
+    net = Oracle(sd)
+    state = siamese_init(frames[0], np.array([x + w / 2, y + h / 2]), np.array([w, h]), net, hp, device="cpu")
+    rec = {"pos": [], "sz": [], "score": [], "mask_area": [], "polygon": []}
+    for f in frames[1:]:
+        state = siamese_track(state, f, mask_enable=True, refine_enable=True, device="cpu")
+        rec["pos"].append(state["target_pos"].copy())
+        rec["sz"].append(state["target_sz"].copy())
+        rec["score"].append(state["score"])
+        rec["mask_area"].append(float((state["mask"] > hp["seg_thr"]).sum()))
+        rec["polygon"].append(np.asarray(state["ploygon"], dtype=np.float64))
+    np.savez_compressed(os.path.join(OUT, "tracker_loop.npz"), **{k: np.asarray(v) for k, v in rec.items()})
+
+
 def main():
     from oracle.calibrate import calibrated_state_dict, synthetic_inputs
     warnings.filterwarnings("ignore")
@@ -69,6 +112,7 @@ def main():
         ks = torch.randn(2, 8, 5, 5, generator=g)
         np.savez_compressed(os.path.join(OUT, "xcorr_small.npz"), x=xs.numpy(), k=ks.numpy(),
                             out=conv2d_dw_group(xs, ks).numpy())
+    tracker_loop_golden(sd)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -121,6 +121,9 @@ void launch_deconv(const float* p3, const float* w, const float* bias, float* ou
                    int cout, cudaStream_t st);
 void launch_split_to_f32(const Act& in, float* out, cudaStream_t st);
 void launch_import_nchw(const float* x_nchw, Act out, cudaStream_t st);
+void launch_select(const float* cls, const float* loc, const float* anchors, const float* window, const float* tsz,
+                   int B, int A, int R, double penalty_k, double window_influence, int32_t* best_idx, int32_t* pos,
+                   float* rec, cudaStream_t st);
 // small-channel fp32 NHWC 3x3 pad-1 conv: in = up(a (+ b)); ymap/xmap: device nearest-upsample source indices
 void launch_small_conv3x3_maps(const float* a, const float* b, int B, int Hi, int Wi, int Ho, int Wo, int Cin, int Cout,
                                const int* ymap, const int* xmap, const float* w, const float* bias, int relu,

@@ -1090,6 +1090,19 @@ int sm_conv2d(const float* x, const float* w, const float* scale, const float* s
   SM_API_END
 }
 
+int sm_select(sm_engine* e, int32_t B, const float* cls, const float* loc, const float* anchors, const float* window,
+              const float* target_sz_in_crop, double penalty_k, double window_influence, int32_t* best_idx, int32_t* pos,
+              float* records, void* stream) {
+  SM_API_BEGIN
+  SMK_CHECK(e && cls && loc && anchors && window && target_sz_in_crop && best_idx && pos && records, "null argument");
+  SMK_CHECK(B >= 1, "batch");
+  const sm_config& c = e->impl->cfg();
+  const int R = (c.search_size - 127) / 8 + 9;
+  smk::launch_select(cls, loc, anchors, window, target_sz_in_crop, B, c.anchor_num, R, penalty_k, window_influence,
+                     best_idx, pos, records, static_cast<cudaStream_t>(stream));
+  SM_API_END
+}
+
 int sm_export(sm_engine* e, const char* what, float* out, int64_t* shape4, void* stream) {
   SM_API_BEGIN
   SMK_CHECK(e && what, "null argument");

@@ -509,6 +509,92 @@ __global__ void __launch_bounds__(256) small_conv3x3_kernel(const float* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Score / box post-processing of siamese_track (tools/test.py:205-254), one block per tracker stream:
+//   score = softmax(cls)[:,1]; box = anchor decode of loc (:209-212); scale / ratio penalty (:214-232);
+//   pscore = penalty*score*(1-wi) + window*wi (:235-236); argmax (:237, first maximum wins like np.argmax);
+//   (dy, dx) = unravel(best, (A, R, R))[1:] (:253-254).
+// cls f32 [B][2A][R][R], loc f32 [B][4A][R][R], anchors f32 [A*R*R][4] (cx,cy,w,h), window f32 [A*R*R],
+// tsz f32 [B][2] = target_sz * scale_x.  The network part is fp32 as in the reference; the penalty is
+// evaluated in fp64 (numpy promotes those expressions to float64 through the float64 target size).
+__global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ cls, const float* __restrict__ loc,
+                                                     const float* __restrict__ anchors,
+                                                     const float* __restrict__ window,
+                                                     const float* __restrict__ tsz, int A, int R, double penalty_k,
+                                                     double window_influence, int32_t* __restrict__ best_idx,
+                                                     int32_t* __restrict__ pos, float* __restrict__ rec) {
+  const int b = blockIdx.x;
+  const int RR = R * R, n = A * RR;
+  const float* c = cls + (size_t)b * 2 * A * RR;
+  const float* l = loc + (size_t)b * 4 * A * RR;
+  const double tw = tsz[2 * b], th = tsz[2 * b + 1];
+  const double tpad = (tw + th) * 0.5;
+  const double tsz_c = sqrt((tw + tpad) * (th + tpad));
+  const double tratio = tw / th;
+  double best = -INFINITY;
+  int besti = 0x7fffffff;
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    const int a = idx / RR, p = idx - a * RR;
+    const float s0 = c[(size_t)a * RR + p], s1 = c[(size_t)(A + a) * RR + p];
+    const float m = fmaxf(s0, s1);
+    const float e0 = expf(s0 - m), e1 = expf(s1 - m);
+    const float score = e1 / (e0 + e1);
+    const float aw = anchors[4 * idx + 2], ah = anchors[4 * idx + 3];
+    const float w = expf(l[(size_t)(2 * A + a) * RR + p]) * aw;
+    const float h = expf(l[(size_t)(3 * A + a) * RR + p]) * ah;
+    const float pad = (w + h) * 0.5f;
+    const float sz = sqrtf((w + pad) * (h + pad));
+    double sc = (double)sz / tsz_c;
+    sc = fmax(sc, 1.0 / sc);
+    double rc = tratio / (double)(w / h);
+    rc = fmax(rc, 1.0 / rc);
+    const double penalty = exp(-(rc * sc - 1.0) * penalty_k);
+    const double ps = penalty * (double)score * (1.0 - window_influence) + (double)window[idx] * window_influence;
+    if (ps > best || (ps == best && idx < besti)) { best = ps; besti = idx; }
+  }
+  __shared__ double sv[256];
+  __shared__ int si[256];
+  sv[threadIdx.x] = best;
+  si[threadIdx.x] = besti;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      const double ov = sv[threadIdx.x + s];
+      const int oi = si[threadIdx.x + s];
+      if (ov > sv[threadIdx.x] || (ov == sv[threadIdx.x] && oi < si[threadIdx.x])) { sv[threadIdx.x] = ov; si[threadIdx.x] = oi; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int idx = si[0];
+    const int a = idx / RR, p = idx - a * RR;
+    best_idx[b] = idx;
+    pos[2 * b] = p / R;          // delta_y
+    pos[2 * b + 1] = p % R;      // delta_x
+    const float ax = anchors[4 * idx], ay = anchors[4 * idx + 1], aw = anchors[4 * idx + 2], ah = anchors[4 * idx + 3];
+    const float s0 = c[(size_t)a * RR + p], s1 = c[(size_t)(A + a) * RR + p];
+    const float m = fmaxf(s0, s1);
+    const float e0 = expf(s0 - m), e1 = expf(s1 - m);
+    const float score = e1 / (e0 + e1);
+    const float w = expf(l[(size_t)(2 * A + a) * RR + p]) * aw;
+    const float h = expf(l[(size_t)(3 * A + a) * RR + p]) * ah;
+    const float pad = (w + h) * 0.5f;
+    double sc = (double)sqrtf((w + pad) * (h + pad)) / tsz_c;
+    sc = fmax(sc, 1.0 / sc);
+    double rc = tratio / (double)(w / h);
+    rc = fmax(rc, 1.0 / rc);
+    float* o = rec + 8 * b;
+    o[0] = l[(size_t)a * RR + p] * aw + ax;
+    o[1] = l[(size_t)(A + a) * RR + p] * ah + ay;
+    o[2] = w;
+    o[3] = h;
+    o[4] = score;
+    o[5] = (float)exp(-(rc * sc - 1.0) * penalty_k);
+    o[6] = (float)sv[0];
+    o[7] = 0.f;
+  }
+}
+
 inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
   return (int)(g > 148 * 64 ? 148 * 64 : (g == 0 ? 1 : g));
@@ -609,6 +695,13 @@ void launch_split_to_f32(const Act& in, float* out, cudaStream_t st) {
 
 void launch_import_nchw(const float* x, Act out, cudaStream_t st) {
   import_nchw_kernel<<<grid_for(out.numel(), 256), 256, 0, st>>>(x, out);
+  SMK_CUDA(cudaGetLastError());
+}
+
+void launch_select(const float* cls, const float* loc, const float* anchors, const float* window, const float* tsz,
+                   int B, int A, int R, double penalty_k, double window_influence, int32_t* best_idx, int32_t* pos,
+                   float* rec, cudaStream_t st) {
+  select_kernel<<<B, 256, 0, st>>>(cls, loc, anchors, window, tsz, A, R, penalty_k, window_influence, best_idx, pos, rec);
   SMK_CUDA(cudaGetLastError());
 }
 

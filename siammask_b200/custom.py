@@ -193,6 +193,29 @@ class Custom:
             _lib.check(self._lib.sm_refine(self._engine, B, p.data_ptr(), out.data_ptr(), self._stream()))
         return out
 
+    @torch.no_grad()
+    def select(self, cls, loc, anchors, window, target_sz_in_crop, penalty_k: float, window_influence: float):
+        """On-device restatement of tools/test.py:205-254.  cls/loc: outputs of track/track_mask; anchors f32
+        [A*R*R,4] (cx,cy,w,h) and window f32 [A*R*R] as built by siamese_init; target_sz_in_crop f32 [B,2].
+        Returns (best_idx int32 [B], pos int32 [B,2] = (delta_y, delta_x), records f32 [B,8])."""
+        B = cls.shape[0]
+        dev = self._device
+        anchors = anchors.to(dev, torch.float32).contiguous()
+        window = window.to(dev, torch.float32).contiguous()
+        tsz = target_sz_in_crop.to(dev, torch.float32).reshape(B, 2).contiguous()
+        n = self.anchor_num * self.score_size ** 2
+        if anchors.shape != (n, 4) or window.numel() != n:
+            raise ValueError(f"anchors/window must have {n} entries")
+        best = torch.empty(B, dtype=torch.int32, device=dev)
+        pos = torch.empty(B, 2, dtype=torch.int32, device=dev)
+        rec = torch.empty(B, 8, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.sm_select(self._engine, B, cls.data_ptr(), loc.data_ptr(), anchors.data_ptr(),
+                                           window.data_ptr(), tsz.data_ptr(), float(penalty_k),
+                                           float(window_influence), best.data_ptr(), pos.data_ptr(), rec.data_ptr(),
+                                           self._stream()))
+        return best, pos, rec
+
     # ------------------------------------------------------------------ introspection used by tests / bench
     def export(self, what: str) -> torch.Tensor:
         shape = (C.c_int64 * 4)()
