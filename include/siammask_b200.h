@@ -113,6 +113,11 @@ int sm_conv2d(const float* x, const float* w, const float* scale, const float* s
  * with out == NULL only the shape is returned. */
 int sm_export(sm_engine* e, const char* what, float* out, int64_t* shape4, void* stream);
 
+/* CUDA-graph replay of sm_track / sm_refine (off by default).  A call whose arguments (pointers, batch, flags,
+ * stream) repeat is captured on its second occurrence and replayed afterwards: one graph launch instead of ~80
+ * kernel launches — for the launch-bound small-batch / single-stream tracker loop. */
+int sm_engine_set_graphs(sm_engine* e, int32_t on);
+
 /* Per-launch CUDA-event timing on the caller's stream (bench.py's roofline leg).  While enabled every kernel
  * launch is bracketed by events; sm_profile_dump synchronises and returns tab-separated lines
  * "name\tcategory\tms\tflops\tbytes\n" (algorithmic FLOPs / bytes of that launch) and clears the log.

@@ -42,6 +42,7 @@ SIGNATURES = {
     "sm_xcorr_depthwise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     "sm_conv2d": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 13 + [C.c_void_p]),
     "sm_export": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "sm_engine_set_graphs": (C.c_int, [C.c_void_p, C.c_int32]),
     "sm_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "sm_profile_dump": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "sm_launch_count": (C.c_int64, [C.c_void_p]),

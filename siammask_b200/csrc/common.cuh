@@ -88,6 +88,18 @@ struct CudaError : std::runtime_error {
     if (!(cond)) throw std::runtime_error(std::string("check failed: ") + #cond + " — " + (msg));   \
   } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember, per kernel, on which devices it was
+// already raised (one process may drive several GPUs).
+template <typename K>
+inline void ensure_dynamic_smem(K kernel, int bytes, unsigned long long& done_mask) {
+  int dev = 0;
+  SMK_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done_mask & bit) return;
+  SMK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done_mask |= bit;
+}
+
 // ---- launchers (defined in the .cu files) ---------------------------------------------------
 
 // conv_gemm_sm100.cu : tensor-core implicit GEMM. nsplit = 1 (fast) or 2 planes (exact, 3 MMAs).

@@ -513,11 +513,8 @@ template <int BLOCK_N, int NSPLIT, int BK = 64>
 void launch_cfg(const GemmParams& p, int num_sms, cudaStream_t st) {
   using C = Cfg<BLOCK_N, NSPLIT, BK>;
   auto kern = conv_gemm_kernel<BLOCK_N, NSPLIT, BK>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
+  static unsigned long long attr_done = 0;
+  ensure_dynamic_smem(kern, C::SMEM_BYTES, attr_done);
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms ? tiles : num_sms;
   kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);

@@ -88,6 +88,7 @@ class Engine {
   void do_template(int slot0, int B, const float* z, cudaStream_t st);
   void do_track(int slot0, int B, const float* x, float* cls, float* loc, float* mask, int flags, cudaStream_t st);
   void do_refine(int B, const int32_t* pos, float* out, cudaStream_t st);
+  void set_graphs(bool on) { use_graphs_ = on; }
   void track_host(int slot0, int B, const float* xh, float* clsh, float* loch, const int32_t* posh, float* maskh,
                   cudaStream_t st);
   void do_export(const char* what, float* out, int64_t* shape4, cudaStream_t st);
@@ -168,6 +169,54 @@ class Engine {
   int64_t launches_ = 0;
   size_t total_bytes_ = 0;
   bool measuring_ = false;
+
+  // CUDA-graph replay of a whole track / refine call (launch-bound small batches).  A call signature seen once
+  // runs eagerly, the second time it is captured (all work, including the auxiliary-stream branches, hangs off
+  // the caller's stream) and from then on replayed; the host-side bookkeeping of the call is restored with it.
+  struct GraphEntry {
+    int seen = 0;
+    cudaGraphExec_t exec = nullptr;
+    std::map<std::string, Act> named;
+    int last_B = 0;
+    bool have_mask_feats = false;
+    int64_t launches = 0;
+  };
+  bool use_graphs_ = false;
+  std::map<std::vector<uint64_t>, GraphEntry> graphs_;
+  void track_impl(int slot0, int B, const float* x, float* cls, float* loc, float* mask, int flags, cudaStream_t st);
+  void refine_impl(int B, const int32_t* pos, float* out, cudaStream_t st);
+  template <typename F>
+  void run_with_graph(const std::vector<uint64_t>& key, cudaStream_t st, F&& body) {
+    if (!use_graphs_ || profiling_) { body(); return; }
+    GraphEntry& ge = graphs_[key];
+    if (ge.exec != nullptr) {
+      SMK_CUDA(cudaGraphLaunch(ge.exec, st));
+      for (auto& kv : ge.named) if (kv.first != "zf") named_[kv.first] = kv.second;
+      last_B_ = ge.last_B;
+      have_mask_feats_ = ge.have_mask_feats;
+      launches_ += ge.launches;
+      return;
+    }
+    if (ge.seen++ == 0) { body(); return; }          // first sight: eager (also warms function attributes)
+    const int64_t l0 = launches_;
+    cudaGraph_t graph = nullptr;
+    SMK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    try {
+      body();
+    } catch (...) {
+      cudaStreamEndCapture(st, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    SMK_CUDA(cudaStreamEndCapture(st, &graph));
+    SMK_CUDA(cudaGraphInstantiate(&ge.exec, graph, 0));
+    SMK_CUDA(cudaGraphDestroy(graph));
+    ge.named = named_;
+    ge.last_B = last_B_;
+    ge.have_mask_feats = have_mask_feats_;
+    ge.launches = launches_ - l0;
+    SMK_CUDA(cudaGraphLaunch(ge.exec, st));
+  }
 
   // independent sub-graphs (the three correlation heads; the refine stage's v-branches) run on auxiliary
   // streams forked from / joined back into the caller's stream with events
@@ -412,6 +461,7 @@ Engine::~Engine() {
   for (int i = 0; i < kAux; ++i) if (aux_[i]) cudaStreamDestroy(aux_[i]);
   for (auto e : sync_events_) cudaEventDestroy(e);
   for (auto e : event_pool_) cudaEventDestroy(e);
+  for (auto& kv : graphs_) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
 }
 
 size_t Engine::measure_arena(int B, int S, bool search) {
@@ -727,6 +777,13 @@ void Engine::do_template(int slot0, int B, const float* z, cudaStream_t st) {
 
 void Engine::do_track(int slot0, int B, const float* x, float* cls, float* loc, float* mask, int flags,
                       cudaStream_t st) {
+  const std::vector<uint64_t> key = {1, (uint64_t)slot0, (uint64_t)B, (uint64_t)x, (uint64_t)cls, (uint64_t)loc,
+                                     (uint64_t)mask, (uint64_t)flags, (uint64_t)st};
+  run_with_graph(key, st, [&] { track_impl(slot0, B, x, cls, loc, mask, flags, st); });
+}
+
+void Engine::track_impl(int slot0, int B, const float* x, float* cls, float* loc, float* mask, int flags,
+                        cudaStream_t st) {
   SMK_CHECK(weights_ready_, "weights not loaded");
   SMK_CHECK(B >= 1 && B <= cfg_.max_batch && slot0 >= 0 && slot0 + B <= cfg_.num_slots, "track batch/slot range");
   SMK_CHECK(cls != nullptr && loc != nullptr, "cls/loc outputs required");
@@ -792,6 +849,13 @@ F32T Engine::small(const F32T& a, const F32T* b, int Ho, const ConvW& Lw, bool r
 
 // Refine.forward(test=True), custom.py:131-154, one (dy,dx) per stream
 void Engine::do_refine(int B, const int32_t* pos, float* out, cudaStream_t st) {
+  SMK_CHECK(have_mask_feats_ && B == last_B_, "sm_refine must follow sm_track(..., SM_TRACK_MASK_FEATURES) with the same B");
+  const std::vector<uint64_t> key = {2, (uint64_t)B, (uint64_t)pos, (uint64_t)out, (uint64_t)st,
+                                     (uint64_t)named_["p0"].hi};
+  run_with_graph(key, st, [&] { refine_impl(B, pos, out, st); });
+}
+
+void Engine::refine_impl(int B, const int32_t* pos, float* out, cudaStream_t st) {
   SMK_CHECK(cfg_.with_mask, "engine was built without the mask branch");
   SMK_CHECK(have_mask_feats_ && B == last_B_, "sm_refine must follow sm_track(..., SM_TRACK_MASK_FEATURES) with the same B");
   Arena& ar = refine_arena_;
@@ -1107,6 +1171,13 @@ int sm_export(sm_engine* e, const char* what, float* out, int64_t* shape4, void*
   SM_API_BEGIN
   SMK_CHECK(e && what, "null argument");
   e->impl->do_export(what, out, shape4, static_cast<cudaStream_t>(stream));
+  SM_API_END
+}
+
+int sm_engine_set_graphs(sm_engine* e, int32_t on) {
+  SM_API_BEGIN
+  SMK_CHECK(e, "null argument");
+  e->impl->set_graphs(on != 0);
   SM_API_END
 }
 

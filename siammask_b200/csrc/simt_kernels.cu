@@ -632,20 +632,14 @@ void launch_xcorr_nhwc(const Act& x, const __half* k_hi, const __half* k_lo, int
   // 32 channels per block when the HxW tile fits (29x29 @255: 105 KB), else 16 (45x45 @383: 127 KB)
   const size_t smem32 = (size_t)x.H * x.W * 32 * sizeof(float);
   if (smem32 <= 110 * 1024) {
-    static size_t attr = 0;
-    if (smem32 > attr) {
-      SMK_CUDA(cudaFuncSetAttribute(xcorr_nhwc_kernel<5, 5, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
-      attr = smem32;
-    }
+    static unsigned long long attr = 0;
+    ensure_dynamic_smem(xcorr_nhwc_kernel<5, 5, 32>, 110 * 1024, attr);
     xcorr_nhwc_kernel<5, 5, 32><<<dim3(x.C / 32, x.B), 256, smem32, st>>>(x, k_hi, k_lo, out);
   } else {
     const size_t smem16 = smem32 / 2;
     SMK_CHECK(smem16 <= 220 * 1024, "xcorr input tile does not fit shared memory");
-    static size_t attr = 0;
-    if (smem16 > attr) {
-      SMK_CUDA(cudaFuncSetAttribute(xcorr_nhwc_kernel<5, 5, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-      attr = smem16;
-    }
+    static unsigned long long attr = 0;
+    ensure_dynamic_smem(xcorr_nhwc_kernel<5, 5, 16>, 220 * 1024, attr);
     xcorr_nhwc_kernel<5, 5, 16><<<dim3(x.C / 16, x.B), 256, smem16, st>>>(x, k_hi, k_lo, out);
   }
   SMK_CUDA(cudaGetLastError());

@@ -282,12 +282,12 @@ void launch_stem_tc(const float* x, int B, int S, const __half* w_hi, const __ha
   if (nsplit == 1) { p.tmB[1] = p.tmB[0]; p.tmOut[1] = p.tmOut[0]; }
   const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
   if (nsplit == 2) {
-    static bool attr = false;
-    if (!attr) { SMK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCfg<2>::SMEM)); attr = true; }
+    static unsigned long long attr = 0;
+    ensure_dynamic_smem(stem_tc_kernel<2>, SCfg<2>::SMEM, attr);
     stem_tc_kernel<2><<<grid, NTHREADS, SCfg<2>::SMEM, st>>>(p);
   } else {
-    static bool attr = false;
-    if (!attr) { SMK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCfg<1>::SMEM)); attr = true; }
+    static unsigned long long attr = 0;
+    ensure_dynamic_smem(stem_tc_kernel<1>, SCfg<1>::SMEM, attr);
     stem_tc_kernel<1><<<grid, NTHREADS, SCfg<1>::SMEM, st>>>(p);
   }
   SMK_CUDA(cudaGetLastError());

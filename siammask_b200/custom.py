@@ -31,7 +31,7 @@ DEFAULT_ANCHORS = {"stride": 8, "ratios": [0.33, 0.5, 1, 2, 3], "scales": [8], "
 class Custom:
     def __init__(self, pretrain: bool = False, anchors: dict | None = None, *, search_size: int = 255,
                  max_batch: int = 1, num_slots: int | None = None, precision: str = "exact",
-                 backend: str = "tensor", mask: bool = True, **_unused):
+                 backend: str = "tensor", mask: bool = True, graphs: bool = False, **_unused):
         self.anchors = anchors if anchors is not None else dict(DEFAULT_ANCHORS)      # siammask_sharp.py:16
         self.anchor_num = len(self.anchors["ratios"]) * len(self.anchors["scales"])   # siammask_sharp.py:17
         self.search_size = int(search_size)
@@ -40,6 +40,8 @@ class Custom:
         self.precision = {"exact": _lib.SM_PRECISION_EXACT, "fast": _lib.SM_PRECISION_FAST}[precision]
         self.backend = {"tensor": _lib.SM_BACKEND_TENSOR, "simt": _lib.SM_BACKEND_SIMT}[backend]
         self.with_mask = bool(mask)
+        self.graphs = bool(graphs)          # CUDA-graph replay: persistent I/O buffers, outputs overwritten per call
+        self._io: dict = {}
         self.score_size = (self.search_size - 127) // 8 + 1 + 8            # utils/tracker_config.py:23
         self.training = False
         self._sd: dict[str, torch.Tensor] | None = None
@@ -94,6 +96,9 @@ class Custom:
             cfg = _lib.SmConfig(self.search_size, self.max_batch, self.num_slots, self.precision, self.backend,
                                 self.anchor_num, int(self.with_mask))
             _lib.check(self._lib.sm_engine_create(C.byref(cfg), C.byref(self._engine)))
+            _lib.check(self._lib.sm_engine_set_graphs(self._engine, int(self.graphs)))
+            self._io = {}
+            self._gstream = torch.cuda.Stream(device) if self.graphs else None
             if self._sd is not None:
                 self._upload()
         return self
@@ -136,28 +141,58 @@ class Custom:
             raise ValueError(f"expected [B,3,{size},{size}], got {tuple(t.shape)}")
         if t.shape[0] > self.max_batch:
             raise ValueError(f"batch {t.shape[0]} > max_batch {self.max_batch}")
-        return t.to(self._device, torch.float32).contiguous()
+        t = t.to(self._device, torch.float32).contiguous()
+        if self.graphs:                      # graph replay needs stable addresses: stage into a persistent buffer
+            buf = self._buf(("in", size, t.shape[0]), t.shape, torch.float32)
+            buf.copy_(t)
+            return buf
+        return t
+
+    def _buf(self, key, shape, dtype):
+        if not self.graphs:
+            return torch.empty(*shape, device=self._device, dtype=dtype)
+        b = self._io.get(key)
+        if b is None:
+            b = self._io[key] = torch.empty(*shape, device=self._device, dtype=dtype)
+        return b
 
     def _stream(self):
+        """Stream the engine call is enqueued on.  Graph capture is impossible on the legacy default stream, so in
+        graph mode the work runs on a private stream fenced against the caller's current stream on both sides
+        (`_fence_in` before the call, `_fence_out` after)."""
+        if self.graphs:
+            return C.c_void_p(self._gstream.cuda_stream)
         return C.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
+
+    def _fence_in(self):
+        if self.graphs:
+            self._gstream.wait_stream(torch.cuda.current_stream(self._device))
+
+    def _fence_out(self):
+        if self.graphs:
+            torch.cuda.current_stream(self._device).wait_stream(self._gstream)
 
     @torch.no_grad()
     def template(self, z, slot0: int = 0):
         z = self._prep(z, 127)
         with torch.cuda.device(self._device):
+            self._fence_in()
             _lib.check(self._lib.sm_template(self._engine, slot0, z.shape[0], z.data_ptr(), self._stream()))
+            self._fence_out()
 
     def _track(self, x, slot0, flags):
         x = self._prep(x, self.search_size)
         B, A, R = x.shape[0], self.anchor_num, self.score_size
-        cls = torch.empty(B, 2 * A, R, R, device=self._device, dtype=torch.float32)
-        loc = torch.empty(B, 4 * A, R, R, device=self._device, dtype=torch.float32)
+        cls = self._buf(("cls", B), (B, 2 * A, R, R), torch.float32)
+        loc = self._buf(("loc", B), (B, 4 * A, R, R), torch.float32)
         mask = None
         if flags & _lib.SM_TRACK_MASK_HEAD:
-            mask = torch.empty(B, 63 * 63, R, R, device=self._device, dtype=torch.float32)
+            mask = self._buf(("mask", B), (B, 63 * 63, R, R), torch.float32)
         with torch.cuda.device(self._device):
+            self._fence_in()
             _lib.check(self._lib.sm_track(self._engine, slot0, B, x.data_ptr(), cls.data_ptr(), loc.data_ptr(),
                                           mask.data_ptr() if mask is not None else None, flags, self._stream()))
+            self._fence_out()
         self._last_B = B
         return cls, loc, mask
 
@@ -188,9 +223,15 @@ class Custom:
         p = p.contiguous()
         if p.shape[0] != B:
             raise ValueError(f"pos has {p.shape[0]} rows, last track had batch {B}")
-        out = torch.empty(B, 127 * 127, device=self._device, dtype=torch.float32)
+        if self.graphs:
+            pb = self._buf(("pos", B), (B, 2), torch.int32)
+            pb.copy_(p)
+            p = pb
+        out = self._buf(("refine", B), (B, 127 * 127), torch.float32)
         with torch.cuda.device(self._device):
+            self._fence_in()
             _lib.check(self._lib.sm_refine(self._engine, B, p.data_ptr(), out.data_ptr(), self._stream()))
+            self._fence_out()
         return out
 
     @torch.no_grad()
@@ -210,10 +251,12 @@ class Custom:
         pos = torch.empty(B, 2, dtype=torch.int32, device=dev)
         rec = torch.empty(B, 8, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
+            self._fence_in()
             _lib.check(self._lib.sm_select(self._engine, B, cls.data_ptr(), loc.data_ptr(), anchors.data_ptr(),
                                            window.data_ptr(), tsz.data_ptr(), float(penalty_k),
                                            float(window_influence), best.data_ptr(), pos.data_ptr(), rec.data_ptr(),
                                            self._stream()))
+            self._fence_out()
         return best, pos, rec
 
     # ------------------------------------------------------------------ introspection used by tests / bench
@@ -222,7 +265,9 @@ class Custom:
         with torch.cuda.device(self._device):
             _lib.check(self._lib.sm_export(self._engine, what.encode(), None, shape, self._stream()))
             out = torch.empty(*[int(s) for s in shape], device=self._device, dtype=torch.float32)
+            self._fence_in()
             _lib.check(self._lib.sm_export(self._engine, what.encode(), out.data_ptr(), shape, self._stream()))
+            self._fence_out()
         return out
 
     def profile(self, on: bool):

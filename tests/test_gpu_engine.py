@@ -144,3 +144,23 @@ def test_errors_are_loud(calib_sd):
     m.track_mask(x.cuda())
     with pytest.raises(IndexError):
         m.track_refine((25, 0))
+
+
+def test_graph_replay_matches_eager(calib_sd):
+    """CUDA-graph replay (sm_engine_set_graphs): call 1 eager, call 2 captured, calls 3+ replayed — same results,
+    fresh inputs are honoured (persistent staging buffers), refine positions too."""
+    z, x = synthetic_inputs(41, 2)
+    _, x2 = synthetic_inputs(42, 2)
+    eager = _engine(calib_sd, max_batch=2)
+    eager.template(z.cuda())
+    g = _engine(calib_sd, max_batch=2, graphs=True)
+    g.template(z.cuda())
+    for it, xin in enumerate([x, x2, x, x2, x]):
+        ce, le, _ = eager.track_mask(xin.cuda(), mask_head=False)
+        cg, lg, _ = g.track_mask(xin.cuda(), mask_head=False)
+        pos = np.array([[3 + it, 5], [20, 2 + it]])
+        re_, rg = eager.track_refine(pos), g.track_refine(pos)
+        assert_close(cg, ce, 1e-6, f"graph cls call {it}")
+        assert_close(lg, le, 1e-6, f"graph loc call {it}")
+        assert_close(rg, re_, 1e-6, f"graph refine call {it}")
+    assert g.launch_count == eager.launch_count
