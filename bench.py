@@ -271,25 +271,36 @@ def run_gpu(args, rank, local_rank, world):
     xh = [torch.empty(B, 3, S, S).pin_memory() for _ in range(2)]
     for t in xh:
         t.copy_(xs[0].cpu())
-    clsh = torch.empty(B, 2 * A, R, R).pin_memory()
-    loch = torch.empty(B, 4 * A, R, R).pin_memory()
-    maskh = torch.empty(B, 127 * 127).pin_memory()
-    posh = pos.cpu().contiguous()
+    clsh = [torch.empty(B, 2 * A, R, R).pin_memory() for _ in range(2)]
+    loch = [torch.empty(B, 4 * A, R, R).pin_memory() for _ in range(2)]
+    maskh = [torch.empty(B, 127 * 127).pin_memory() for _ in range(2)]
+    posh = pos.cpu().contiguous().pin_memory()
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
-    def host_step(i):
-        _lib.check(lib.sm_track_host(m.handle, 0, B, xh[i % 2].data_ptr(), clsh.data_ptr(), loch.data_ptr(),
-                                     posh.data_ptr(), maskh.data_ptr(), stream))
-    for i in range(3):
-        host_step(i)
+    def submit(i):
+        tk = C.c_int32()
+        _lib.check(lib.sm_track_host_async(m.handle, 0, B, xh[i % 2].data_ptr(), clsh[i % 2].data_ptr(),
+                                           loch[i % 2].data_ptr(), posh.data_ptr(), maskh[i % 2].data_ptr(), stream,
+                                           C.byref(tk)))
+        return tk.value
+
+    def host_loop(n):
+        # a user with a stream of frames keeps one step in flight: submit frame k+1, then collect frame k
+        prev = None
+        for i in range(n):
+            tk = submit(i)
+            if prev is not None:
+                _lib.check(lib.sm_track_host_wait(m.handle, prev))
+            prev = tk
+        _lib.check(lib.sm_track_host_wait(m.handle, prev))
+    host_loop(3)
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        host_step(i)          # synchronises the stream itself (results are in host memory on return)
+    host_loop(args.steps)      # every step's results are in host memory when this returns
     dt = max_over_ranks(time.perf_counter() - t0, device=dev)
     e2e_fps = world * B * args.steps / dt
     h2d = xh[0].numel() * 4 + posh.numel() * 4
-    d2h = (clsh.numel() + loch.numel() + maskh.numel()) * 4
+    d2h = (clsh[0].numel() + loch[0].numel() + maskh[0].numel()) * 4
 
     if rank != 0:
         if world > 1:
@@ -368,7 +379,8 @@ def run_gpu(args, rank, local_rank, world):
         "algorithmic_tflops": fps * GFLOP_PER_FRAME.get(S, 0.0) / 1e3,
         "value_skip_dead_mask_head": fps_skip,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "sm_track_host (C ABI, pinned host buffers; mask head skipped as under --refine)"},
+                "api": "sm_track_host_async / sm_track_host_wait (C ABI, pinned host buffers, one step in flight; "
+                       "refine positions supplied by the host; mask head skipped as under --refine)"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,

@@ -96,6 +96,14 @@ int sm_select(sm_engine* e, int32_t B, const float* cls, const float* loc, const
 int sm_track_host(sm_engine* e, int32_t slot0, int32_t B, const float* x_host, float* cls_host, float* loc_host,
                   const int32_t* pos_host, float* mask_out_host, void* stream);
 
+/* Asynchronous form of sm_track_host: returns at once with a ticket (0/1); sm_track_host_wait(ticket) blocks
+ * until that step's results are in the host buffers.  Two staging sets alternate, so submitting step k+1 before
+ * waiting for step k overlaps its H2D (and step k's D2H) with compute.  Host buffers must stay valid (and pinned,
+ * for real overlap) until the wait returns. */
+int sm_track_host_async(sm_engine* e, int32_t slot0, int32_t B, const float* x_host, float* cls_host, float* loc_host,
+                        const int32_t* pos_host, float* mask_out_host, void* stream, int32_t* ticket);
+int sm_track_host_wait(sm_engine* e, int32_t ticket);
+
 /* conv2d_dw_group — models/rpn.py:32-38, standalone: x f32 [B,C,H,W], k f32 [B,C,kh,kw] ->
  * out f32 [B,C,H-kh+1,W-kw+1], all device pointers. */
 int sm_xcorr_depthwise(const float* x, const float* k, float* out, int32_t B, int32_t C, int32_t H, int32_t W,

@@ -91,6 +91,9 @@ class Engine {
   void set_graphs(bool on) { use_graphs_ = on; }
   void track_host(int slot0, int B, const float* xh, float* clsh, float* loch, const int32_t* posh, float* maskh,
                   cudaStream_t st);
+  int track_host_async(int slot0, int B, const float* xh, float* clsh, float* loch, const int32_t* posh, float* maskh,
+                       cudaStream_t st);
+  void host_wait(int ticket);
   void do_export(const char* what, float* out, int64_t* shape4, cudaStream_t st);
 
   void set_profiling(bool on) { profiling_ = on; }
@@ -153,11 +156,16 @@ class Engine {
   __half* kcache_lo_ = nullptr;
   int n_branches_ = 2;
   // host-path staging
-  float* stage_x_ = nullptr;
-  float* stage_cls_ = nullptr;
-  float* stage_loc_ = nullptr;
-  float* stage_mask_ = nullptr;
-  int32_t* stage_pos_ = nullptr;
+  // two sets (ping-pong) so the H2D of step k+1 and the D2H of step k overlap the compute of the other step
+  float* stage_x_[2] = {nullptr, nullptr};
+  float* stage_cls_[2] = {nullptr, nullptr};
+  float* stage_loc_[2] = {nullptr, nullptr};
+  float* stage_mask_[2] = {nullptr, nullptr};
+  int32_t* stage_pos_[2] = {nullptr, nullptr};
+  cudaStream_t h2d_stream_ = nullptr, d2h_stream_ = nullptr;
+  cudaEvent_t h2d_done_[2] = {nullptr, nullptr}, compute_done_[2] = {nullptr, nullptr}, d2h_done_[2] = {nullptr, nullptr};
+  bool set_busy_[2] = {false, false};
+  uint64_t host_calls_ = 0;
   int* maps_dev_ = nullptr;
   std::map<int, const int*> maps_;
 
@@ -419,11 +427,18 @@ Engine::Engine(const sm_config& cfg) : cfg_(cfg), exact_(cfg.precision == SM_PRE
   SMK_CUDA(cudaMemset(kcache_lo_, 0, kc * sizeof(__half)));
 
   const size_t B = cfg.max_batch, S = cfg.search_size, A = cfg.anchor_num;
-  SMK_CUDA(cudaMalloc(&stage_x_, B * 3 * S * S * sizeof(float)));
-  SMK_CUDA(cudaMalloc(&stage_cls_, B * 2 * A * R_ * R_ * sizeof(float)));
-  SMK_CUDA(cudaMalloc(&stage_loc_, B * 4 * A * R_ * R_ * sizeof(float)));
-  SMK_CUDA(cudaMalloc(&stage_mask_, B * 127 * 127 * sizeof(float)));
-  SMK_CUDA(cudaMalloc(&stage_pos_, B * 2 * sizeof(int32_t)));
+  for (int i = 0; i < 2; ++i) {
+    SMK_CUDA(cudaMalloc(&stage_x_[i], B * 3 * S * S * sizeof(float)));
+    SMK_CUDA(cudaMalloc(&stage_cls_[i], B * 2 * A * R_ * R_ * sizeof(float)));
+    SMK_CUDA(cudaMalloc(&stage_loc_[i], B * 4 * A * R_ * R_ * sizeof(float)));
+    SMK_CUDA(cudaMalloc(&stage_mask_[i], B * 127 * 127 * sizeof(float)));
+    SMK_CUDA(cudaMalloc(&stage_pos_[i], B * 2 * sizeof(int32_t)));
+    SMK_CUDA(cudaEventCreateWithFlags(&h2d_done_[i], cudaEventDisableTiming));
+    SMK_CUDA(cudaEventCreateWithFlags(&compute_done_[i], cudaEventDisableTiming));
+    SMK_CUDA(cudaEventCreateWithFlags(&d2h_done_[i], cudaEventDisableTiming));
+  }
+  SMK_CUDA(cudaStreamCreateWithFlags(&h2d_stream_, cudaStreamNonBlocking));
+  SMK_CUDA(cudaStreamCreateWithFlags(&d2h_stream_, cudaStreamNonBlocking));
 
   // nearest-upsample index tables (custom.py:150-152) + identity tables
   const int pairs[6][2] = {{31, 15}, {61, 31}, {127, 61}, {15, 15}, {31, 31}, {61, 61}};
@@ -442,7 +457,7 @@ Engine::Engine(const sm_config& cfg) : cfg_(cfg), exact_(cfg.precision == SM_PRE
   for (auto& e : sync_events_) SMK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
   total_bytes_ = blob_bytes_ + search_arena_.cap + templ_arena_.cap + refine_arena_.cap + 2 * kc * sizeof(__half) +
-                 (B * 3 * S * S + B * 6 * A * R_ * R_ + B * 127 * 127) * sizeof(float);
+                 2 * (B * 3 * S * S + B * 6 * A * R_ * R_ + B * 127 * 127) * sizeof(float);
 }
 
 Engine::~Engine() {
@@ -452,11 +467,14 @@ Engine::~Engine() {
   cudaFree(refine_arena_.base);
   cudaFree(kcache_hi_);
   cudaFree(kcache_lo_);
-  cudaFree(stage_x_);
-  cudaFree(stage_cls_);
-  cudaFree(stage_loc_);
-  cudaFree(stage_mask_);
-  cudaFree(stage_pos_);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(stage_x_[i]); cudaFree(stage_cls_[i]); cudaFree(stage_loc_[i]); cudaFree(stage_mask_[i]); cudaFree(stage_pos_[i]);
+    if (h2d_done_[i]) cudaEventDestroy(h2d_done_[i]);
+    if (compute_done_[i]) cudaEventDestroy(compute_done_[i]);
+    if (d2h_done_[i]) cudaEventDestroy(d2h_done_[i]);
+  }
+  if (h2d_stream_) cudaStreamDestroy(h2d_stream_);
+  if (d2h_stream_) cudaStreamDestroy(d2h_stream_);
   cudaFree(maps_dev_);
   for (int i = 0; i < kAux; ++i) if (aux_[i]) cudaStreamDestroy(aux_[i]);
   for (auto e : sync_events_) cudaEventDestroy(e);
@@ -917,21 +935,45 @@ void Engine::refine_impl(int B, const int32_t* pos, float* out, cudaStream_t st)
   small(h0b, &v0b, 127, L(R + "post2"), false, out, ar, st);                // (B,127,127,1) == (B,127*127)
 }
 
-void Engine::track_host(int slot0, int B, const float* xh, float* clsh, float* loch, const int32_t* posh, float* maskh,
-                        cudaStream_t st) {
+// Host-buffer step, asynchronous: H2D on a copy stream, compute on the caller's stream, D2H on a second copy
+// stream, chained by events.  Two staging sets alternate, so submitting step k+1 before waiting for step k overlaps
+// its input transfer (and step k's result transfer) with compute.  Returns the ticket to pass to host_wait().
+int Engine::track_host_async(int slot0, int B, const float* xh, float* clsh, float* loch, const int32_t* posh,
+                             float* maskh, cudaStream_t st) {
   const size_t S = cfg_.search_size, A = cfg_.anchor_num;
   const size_t nx = (size_t)B * 3 * S * S, ncls = (size_t)B * 2 * A * R_ * R_, nloc = 2 * ncls;
-  SMK_CUDA(cudaMemcpyAsync(stage_x_, xh, nx * sizeof(float), cudaMemcpyHostToDevice, st));
+  SMK_CHECK(B >= 1 && B <= cfg_.max_batch, "batch");
+  const int t = (int)(host_calls_++ & 1);
+  if (set_busy_[t]) host_wait(t);                 // the staging set is still owned by an un-waited ticket
   const bool refine = posh != nullptr && maskh != nullptr;
-  do_track(slot0, B, stage_x_, stage_cls_, stage_loc_, nullptr, refine ? SM_TRACK_MASK_FEATURES : 0, st);
-  SMK_CUDA(cudaMemcpyAsync(clsh, stage_cls_, ncls * sizeof(float), cudaMemcpyDeviceToHost, st));
-  SMK_CUDA(cudaMemcpyAsync(loch, stage_loc_, nloc * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (refine) {
-    SMK_CUDA(cudaMemcpyAsync(stage_pos_, posh, (size_t)B * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    do_refine(B, stage_pos_, stage_mask_, st);
-    SMK_CUDA(cudaMemcpyAsync(maskh, stage_mask_, (size_t)B * 127 * 127 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  }
-  SMK_CUDA(cudaStreamSynchronize(st));
+  SMK_CUDA(cudaMemcpyAsync(stage_x_[t], xh, nx * sizeof(float), cudaMemcpyHostToDevice, h2d_stream_));
+  if (refine)
+    SMK_CUDA(cudaMemcpyAsync(stage_pos_[t], posh, (size_t)B * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, h2d_stream_));
+  SMK_CUDA(cudaEventRecord(h2d_done_[t], h2d_stream_));
+  SMK_CUDA(cudaStreamWaitEvent(st, h2d_done_[t], 0));
+  do_track(slot0, B, stage_x_[t], stage_cls_[t], stage_loc_[t], nullptr, refine ? SM_TRACK_MASK_FEATURES : 0, st);
+  if (refine) do_refine(B, stage_pos_[t], stage_mask_[t], st);
+  SMK_CUDA(cudaEventRecord(compute_done_[t], st));
+  SMK_CUDA(cudaStreamWaitEvent(d2h_stream_, compute_done_[t], 0));
+  SMK_CUDA(cudaMemcpyAsync(clsh, stage_cls_[t], ncls * sizeof(float), cudaMemcpyDeviceToHost, d2h_stream_));
+  SMK_CUDA(cudaMemcpyAsync(loch, stage_loc_[t], nloc * sizeof(float), cudaMemcpyDeviceToHost, d2h_stream_));
+  if (refine)
+    SMK_CUDA(cudaMemcpyAsync(maskh, stage_mask_[t], (size_t)B * 127 * 127 * sizeof(float), cudaMemcpyDeviceToHost, d2h_stream_));
+  SMK_CUDA(cudaEventRecord(d2h_done_[t], d2h_stream_));
+  set_busy_[t] = true;
+  return t;
+}
+
+void Engine::host_wait(int ticket) {
+  SMK_CHECK(ticket == 0 || ticket == 1, "bad ticket");
+  if (!set_busy_[ticket]) return;
+  SMK_CUDA(cudaEventSynchronize(d2h_done_[ticket]));
+  set_busy_[ticket] = false;
+}
+
+void Engine::track_host(int slot0, int B, const float* xh, float* clsh, float* loch, const int32_t* posh, float* maskh,
+                        cudaStream_t st) {
+  host_wait(track_host_async(slot0, B, xh, clsh, loch, posh, maskh, st));
 }
 
 void Engine::do_export(const char* what, float* out, int64_t* shape4, cudaStream_t st) {
@@ -1129,6 +1171,22 @@ int sm_track_host(sm_engine* e, int32_t slot0, int32_t B, const float* x_host, f
   SM_API_BEGIN
   SMK_CHECK(e && x_host && cls_host && loc_host, "null argument");
   e->impl->track_host(slot0, B, x_host, cls_host, loc_host, pos_host, mask_out_host, static_cast<cudaStream_t>(stream));
+  SM_API_END
+}
+
+int sm_track_host_async(sm_engine* e, int32_t slot0, int32_t B, const float* x_host, float* cls_host, float* loc_host,
+                        const int32_t* pos_host, float* mask_out_host, void* stream, int32_t* ticket) {
+  SM_API_BEGIN
+  SMK_CHECK(e && x_host && cls_host && loc_host && ticket, "null argument");
+  *ticket = e->impl->track_host_async(slot0, B, x_host, cls_host, loc_host, pos_host, mask_out_host,
+                                      static_cast<cudaStream_t>(stream));
+  SM_API_END
+}
+
+int sm_track_host_wait(sm_engine* e, int32_t ticket) {
+  SM_API_BEGIN
+  SMK_CHECK(e, "null argument");
+  e->impl->host_wait(ticket);
   SM_API_END
 }
 

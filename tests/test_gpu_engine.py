@@ -164,3 +164,46 @@ def test_graph_replay_matches_eager(calib_sd):
         assert_close(lg, le, 1e-6, f"graph loc call {it}")
         assert_close(rg, re_, 1e-6, f"graph refine call {it}")
     assert g.launch_count == eager.launch_count
+
+
+def test_host_buffer_path_sync_and_async(calib_sd):
+    """sm_track_host (synchronous) and the pipelined sm_track_host_async / _wait pair deliver the same results as
+    the device-pointer API."""
+    import ctypes as C
+    from siammask_b200 import _lib
+    lib = _lib.load()
+    z, x = synthetic_inputs(51, 2)
+    _, x2 = synthetic_inputs(52, 2)
+    m = _engine(calib_sd, max_batch=2)
+    m.template(z.cuda())
+    pos = torch.tensor([[4, 9], [17, 3]], dtype=torch.int32)
+    want = []
+    for xin in (x, x2):
+        cls, loc, _ = m.track_mask(xin.cuda(), mask_head=False)
+        want.append((cls.cpu(), loc.cpu(), m.track_refine(pos.cuda()).cpu()))
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    xs = [x.contiguous().pin_memory(), x2.contiguous().pin_memory()]
+    outs = [(torch.empty(2, 10, 25, 25).pin_memory(), torch.empty(2, 20, 25, 25).pin_memory(),
+             torch.empty(2, 127 * 127).pin_memory()) for _ in range(2)]
+    posh = pos.contiguous().pin_memory()
+    # synchronous
+    for i in range(2):
+        _lib.check(lib.sm_track_host(m.handle, 0, 2, xs[i].data_ptr(), outs[i][0].data_ptr(), outs[i][1].data_ptr(),
+                                     posh.data_ptr(), outs[i][2].data_ptr(), st))
+        for got, ref, n in zip(outs[i], want[i], ("cls", "loc", "refine")):
+            assert_close(got, ref, 1e-6, f"sync host path {n} step {i}")
+    # pipelined: submit both steps, then collect
+    for o in outs:
+        for t in o:
+            t.zero_()
+    tickets = []
+    for i in range(2):
+        tk = C.c_int32()
+        _lib.check(lib.sm_track_host_async(m.handle, 0, 2, xs[i].data_ptr(), outs[i][0].data_ptr(),
+                                           outs[i][1].data_ptr(), posh.data_ptr(), outs[i][2].data_ptr(), st, C.byref(tk)))
+        tickets.append(tk.value)
+    assert tickets == [0, 1] or tickets == [1, 0]
+    for i in range(2):
+        _lib.check(lib.sm_track_host_wait(m.handle, tickets[i]))
+        for got, ref, n in zip(outs[i], want[i], ("cls", "loc", "refine")):
+            assert_close(got, ref, 1e-6, f"async host path {n} step {i}")
