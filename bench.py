@@ -319,7 +319,7 @@ def run_gpu(args, rank, local_rank, world):
     for name, cat, t, fl, by in rows:
         c = cats.setdefault(cat, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
         c["ms"] += t / nprof; c["flops"] += fl / nprof; c["bytes"] += by / nprof; c["launches"] += 1 / nprof
-    gemm = cats.get("conv_gemm", {"ms": 1e-9, "flops": 0.0, "launches": 0})
+    gemm = cats.get("conv_gemm", {"ms": 1e-9, "flops": 0.0, "bytes": 0.0, "launches": 0})
     tot_ms = sum(c["ms"] for c in cats.values())
     achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
     layers = {}
@@ -334,10 +334,17 @@ def run_gpu(args, rank, local_rank, world):
             for name, cat, t, fl, by in rows[:len(rows) // nprof]:
                 f.write(f"{name}\t{cat}\t{t:.4f}\t{fl / 1e9:.2f}\t{by / 1e6:.1f}\t{fl / (t * 1e-3) / 1e12:.1f}\t"
                         f"{by / (t * 1e-3) / 1e9:.0f}\n")
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and args.precision == "exact" and B == 64 and S == 255:
+        tj = json.load(open(tpath))           # ncu dram__bytes_read+write of the family's launches in one step
+        traffic = {"bytes_per_step": tj["conv_gemm_traffic_bytes_per_step"],
+                   "launches_per_step": tj["conv_gemm_launches_per_step"], "source": "profiles/r01_traffic.json (ncu)"}
     roofline = {
         "bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv family, all layers of one step)",
         "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-        "peak_source": peaks["src"] + ", sustained cuBLAS bf16", "traffic": None,
+        "peak_source": peaks["src"] + ", sustained cuBLAS bf16", "traffic": traffic,
+        "algorithmic_bytes_per_step": gemm["bytes"],
         "launches_per_step": gemm["launches"], "ms_per_step": gemm["ms"], "share_of_step": gemm["ms"] / tot_ms,
         "algorithmic_gflop_per_step": gemm["flops"] / 1e9,
         "note": "algorithmic FLOPs (2*M*N*K per conv, no padding, no x3 for the split-fp16 passes) / summed "
