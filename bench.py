@@ -208,9 +208,10 @@ def run_gpu(args, rank, local_rank, world):
     # weak scaling: args.batch streams per GPU; this rank owns a contiguous block of the global stream ids
     B = len(shard_streams(args.batch * world, world, rank))
     R = (S - 127) // 8 + 9
-    m = smb.Custom(anchors=smb.DEFAULT_ANCHORS, search_size=S, max_batch=B, num_slots=B, precision=args.precision)
+    m = smb.Custom(anchors=smb.DEFAULT_ANCHORS, search_size=S, max_batch=B, num_slots=B, precision=args.precision,
+                   mask=not args.rpn_only)
     if rank == 0:
-        m.load_state_dict(smb.synthetic_state_dict(0))
+        m.load_state_dict(smb.synthetic_state_dict(0, mask=not args.rpn_only, refine=not args.rpn_only))
     m.eval().to(dev)
     if world > 1:                       # the one collective of the whole job: weights, once, at init
         broadcast_weights(m.weight_blob(), src=0)
@@ -228,7 +229,13 @@ def run_gpu(args, rank, local_rank, world):
     tsz_dev = torch.rand(B, 2, device=dev, generator=gen) * 60 + 30
     m.template(z)
 
+    def step_rpn(i, mask_head=True):
+        cls, loc = m.track(xs[i % 4])
+        return m.select(cls, loc, anchors_dev, window_dev, tsz_dev, 0.04, 0.4)
+
     def step(i, mask_head=True):
+        if args.rpn_only:
+            return step_rpn(i)
         # the full per-frame path of siamese_track (tools/test.py:201-261) without leaving the device:
         # track_mask -> score/box post-processing + argmax -> track_refine at the selected position
         cls, loc, mask = m.track_mask(xs[i % 4], mask_head=mask_head)
@@ -264,6 +271,19 @@ def run_gpu(args, rank, local_rank, world):
     fps = world * B * args.steps / (ms * 1e-3)
     ms_skip = timed(lambda i: step(i, mask_head=False), args.steps)
     fps_skip = world * B * args.steps / (ms_skip * 1e-3)
+
+    if args.rpn_only:
+        if rank == 0:
+            gfl = {255: 30.811, 383: 71.139}.get(S, 0.0)
+            print(json.dumps({"metric": METRIC.replace("SiamMask-sharp", "SiamRPN-only"), "value": fps, "unit": "frames/s",
+                              "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                              "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                              "vs_baseline": None, "precision_mode": args.precision, "data": "synthetic",
+                              "config": {"workload": f"SiamRPN-only track + on-device selection, search {S}, {B} streams/GPU"},
+                              "algorithmic_tflops": fps * gfl / 1e3, "gpu_launches": launches, "clocks": clocks}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D of x, track + refine, D2H of results
     lib = _lib.load()
@@ -412,6 +432,8 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="paired tracker streams per GPU")
     ap.add_argument("--search", type=int, default=255)
     ap.add_argument("--precision", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--rpn-only", action="store_true",
+                    help="SiamRPN-only engine (experiments/siamrpn_resnet): step = track -> cls/loc (BASELINE configs[2])")
     ap.add_argument("--ref-batch", type=int, default=2, help="frames per step of the CPU reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--dump-layers", default=None, help="write the per-launch CUDA-event table of one step here")

@@ -81,6 +81,14 @@ int sm_track(sm_engine* e, int32_t slot0, int32_t B, const float* x_nchw, float*
  * sm_track(..., SM_TRACK_MASK_FEATURES) with the same B. */
 int sm_refine(sm_engine* e, int32_t B, const int32_t* pos, float* out, void* stream);
 
+/* get_subwindow_tracking — tools/test.py:67-110 — on the device: frames uint8 HWC (BGR as cv2.imread returns them),
+ * frame b at frames + b*frame_stride (stride 0 = all streams share one frame); boxes int32 [B][8] (device) =
+ * {context_xmin, context_ymin, original_sz, uint8(avg_chans[0..2]), 0, 0} in frame coordinates BEFORE padding (the
+ * window may leave the frame; those pixels take the average colour, :89-100).  Resizes original_sz -> model_size
+ * bit-exactly like cv2.resize(INTER_LINEAR) on 8-bit data and writes out f32 [B][3][model][model] (:61-64). */
+int sm_crop_resize(const uint8_t* frames, size_t frame_stride, int32_t H, int32_t W, const int32_t* boxes, int32_t B,
+                   int32_t model_size, float* out, void* stream);
+
 /* Score / box post-processing + argmax of siamese_track — tools/test.py:205-254 — on the device, so that
  * sm_track -> sm_select -> sm_refine needs no host round trip.  All pointers are device pointers:
  * cls/loc as returned by sm_track; anchors f32 [A*R*R][4] = (cx,cy,w,h) in generate_anchor order (tools/test.py:113-129);

@@ -595,6 +595,61 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ c
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// get_subwindow_tracking on the device (tools/test.py:67-110): crop a sz x sz window whose top-left corner is
+// (xmin, ymin) in frame coordinates (may lie outside: those pixels take uint8(avg_chans), :89-100), resize it to
+// model x model exactly like cv2.resize(INTER_LINEAR) does for 8-bit images — OpenCV's fixed-point scheme
+// (resize.cpp: 11-bit coefficients, HResizeLinear then VResizeLinear:
+//  dst = (((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2; x fractions are clamped at the borders, y ROWS are) —
+// and emit the float CHW tensor the network consumes (:61-64).  box = int32 [B][8]: xmin, ymin, sz, avg0, avg1, avg2.
+__device__ __forceinline__ void cv_coeff(int d, double scale, int src_n, bool clamp_frac, int& s0, int& a0, int& a1) {
+  float f = (float)(((double)d + 0.5) * scale - 0.5);
+  int s = (int)floorf(f);
+  f -= (float)s;
+  if (clamp_frac) {
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= src_n - 1) { f = 0.f; s = src_n - 1; }
+  }
+  s0 = s;
+  a0 = __float2int_rn((1.f - f) * 2048.f);
+  a1 = __float2int_rn(f * 2048.f);
+}
+
+__global__ void crop_resize_kernel(const uint8_t* __restrict__ frames, size_t frame_stride, int H, int W,
+                                   const int32_t* __restrict__ box, int model, float* __restrict__ out) {
+  const int b = blockIdx.z;
+  const int dx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int dy = blockIdx.y * blockDim.y + threadIdx.y;
+  if (dx >= model || dy >= model) return;
+  const int32_t* bx = box + 8 * b;
+  const int xmin = bx[0], ymin = bx[1], sz = bx[2];
+  const uint8_t* fr = frames + (size_t)b * frame_stride;
+  auto px = [&](int y, int x, int c) -> int {      // pixel of the (virtual, padded) patch
+    const int fy = y + ymin, fx = x + xmin;
+    if (fy < 0 || fy >= H || fx < 0 || fx >= W) return bx[3 + c];
+    return fr[((size_t)fy * W + fx) * 3 + c];
+  };
+  float* o = out + (size_t)b * 3 * model * model + (size_t)dy * model + dx;
+  if (sz == model) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[(size_t)c * model * model] = (float)px(dy, dx, c);
+    return;
+  }
+  const double scale = 1.0 / ((double)model / (double)sz);
+  int sx, ax0, ax1, sy, by0, by1;
+  cv_coeff(dx, scale, sz, true, sx, ax0, ax1);
+  cv_coeff(dy, scale, sz, false, sy, by0, by1);
+  const int x1 = min(sx + 1, sz - 1);
+  const int y0 = min(max(sy, 0), sz - 1), y1 = min(max(sy + 1, 0), sz - 1);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int h0 = px(y0, sx, c) * ax0 + px(y0, x1, c) * ax1;
+    const int h1 = px(y1, sx, c) * ax0 + px(y1, x1, c) * ax1;
+    const int v = (((by0 * (h0 >> 4)) >> 16) + ((by1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    o[(size_t)c * model * model] = (float)min(max(v, 0), 255);
+  }
+}
+
 inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
   return (int)(g > 148 * 64 ? 148 * 64 : (g == 0 ? 1 : g));
@@ -696,6 +751,13 @@ void launch_select(const float* cls, const float* loc, const float* anchors, con
                    int B, int A, int R, double penalty_k, double window_influence, int32_t* best_idx, int32_t* pos,
                    float* rec, cudaStream_t st) {
   select_kernel<<<B, 256, 0, st>>>(cls, loc, anchors, window, tsz, A, R, penalty_k, window_influence, best_idx, pos, rec);
+  SMK_CUDA(cudaGetLastError());
+}
+
+void launch_crop_resize(const uint8_t* frames, size_t frame_stride, int H, int W, const int32_t* box, int B, int model,
+                        float* out, cudaStream_t st) {
+  dim3 block(32, 8), grid((model + 31) / 32, (model + 7) / 8, B);
+  crop_resize_kernel<<<grid, block, 0, st>>>(frames, frame_stride, H, W, box, model, out);
   SMK_CUDA(cudaGetLastError());
 }
 

@@ -60,3 +60,30 @@ def conv2d(x, weight, scale=None, shift=None, stride=1, padding=0, dilation=1, r
                                  sh.data_ptr() if sh is not None else None, out.data_ptr(), B, Cin, H, W, Cout, KH, KW,
                                  stride, padding, dilation, int(relu), be, pr, _stream(dev)))
     return out
+
+
+def crop_resize(frames: torch.Tensor, boxes, model_size: int) -> torch.Tensor:
+    """Device form of get_subwindow_tracking (tools/test.py:67-110).  frames: uint8 CUDA tensor [H,W,3] (shared by all
+    boxes) or [B,H,W,3]; boxes: int [B,6] = (context_xmin, context_ymin, original_sz, avg0, avg1, avg2) in frame
+    coordinates before padding.  Returns f32 [B,3,model,model], bit-identical to the cv2 path."""
+    if not frames.is_cuda or frames.dtype != torch.uint8:
+        raise RuntimeError("crop_resize expects uint8 CUDA frames; there is no CPU path")
+    lib = _lib.load()
+    dev = frames.device
+    frames = frames.contiguous()
+    bx = torch.as_tensor(boxes, dtype=torch.int32).reshape(-1, 6)
+    B = bx.shape[0]
+    full = torch.zeros(B, 8, dtype=torch.int32)
+    full[:, :6] = bx
+    full = full.to(dev)
+    if frames.dim() == 3:
+        H, W, stride = frames.shape[0], frames.shape[1], 0
+    else:
+        if frames.shape[0] != B:
+            raise ValueError("one frame per box expected")
+        H, W, stride = frames.shape[1], frames.shape[2], frames.shape[1] * frames.shape[2] * 3
+    out = torch.empty(B, 3, model_size, model_size, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        _lib.check(lib.sm_crop_resize(frames.data_ptr(), stride, H, W, full.data_ptr(), B, model_size, out.data_ptr(),
+                                      _stream(dev)))
+    return out

@@ -3,8 +3,9 @@
 reference's model API.  With a siammask_b200 engine the score/box post-processing + argmax between `track_mask`
 and `track_refine` (tools/test.py:205-254) runs on the device (`Custom.select`, C ABI `sm_select`), so the only
 host round trip per frame is 8 floats per stream; with any other `net` (e.g. the CPU oracle in the tests) the same
-arithmetic runs in numpy as in the reference.  Crop/resize and mask paste-back stay on the host with cv2, as in the
-reference (get_subwindow_tracking :67-110, crop_back :263-282).
+arithmetic runs in numpy as in the reference.  Frames may be numpy arrays (crop + cv2.resize on the host, as in the
+reference, :67-110) or uint8 CUDA tensors (the crop + a bit-exact restatement of cv2's 8-bit INTER_LINEAR resize run on
+the device, `ops.crop_resize` / C ABI `sm_crop_resize`).  Mask paste-back (crop_back :263-282) stays on the host.
 """
 from __future__ import annotations
 
@@ -89,9 +90,20 @@ def generate_anchor(cfg: dict, score_size: int) -> np.ndarray:
     return anchor
 
 
+def subwindow_box(pos, original_sz, avg_chans):
+    """The integers get_subwindow_tracking derives before touching pixels (tools/test.py:71-76,89-100):
+    (context_xmin, context_ymin, original_sz, uint8(avg_chans))."""
+    c = (original_sz + 1) / 2
+    a = np.asarray(avg_chans, dtype=np.float64).astype(np.uint8)      # numpy assignment into a uint8 image truncates
+    return [int(round(pos[0] - c)), int(round(pos[1] - c)), int(original_sz), int(a[0]), int(a[1]), int(a[2])]
+
+
 def get_subwindow_tracking(im, pos, model_sz, original_sz, avg_chans):
     """tools/test.py:67-110: crop a square window around pos (padding with the frame's mean colour), resize to
     model_sz with cv2.resize, return a float CHW tensor of raw 0..255 pixels."""
+    if isinstance(im, torch.Tensor):         # frame already on the GPU: crop + cv2-exact resize on the device
+        from .ops import crop_resize
+        return crop_resize(im, [subwindow_box(pos, original_sz, avg_chans)], int(model_sz))[0]
     sz = original_sz
     im_sz = im.shape
     c = (original_sz + 1) / 2
@@ -164,7 +176,7 @@ def siamese_init(im, target_pos, target_sz, model, hp=None, device="cuda"):
     p.ratios = model.anchors["ratios"]
     p.anchor_num = model.anchor_num
     p.anchor = generate_anchor(model.anchors, p.score_size)
-    avg_chans = np.mean(im, axis=(0, 1))
+    avg_chans = im.double().mean(dim=(0, 1)).cpu().numpy() if isinstance(im, torch.Tensor) else np.mean(im, axis=(0, 1))
     wc_z = target_sz[0] + p.context_amount * sum(target_sz)
     hc_z = target_sz[1] + p.context_amount * sum(target_sz)
     s_z = round(np.sqrt(wc_z * hc_z))
