@@ -133,6 +133,40 @@ class Custom:
     def adopt_weights(self):
         _lib.check(self._lib.sm_engine_adopt_weights(self._engine))
 
+    # packed-weight file: BN-folded, repacked, fp16-split arena exactly as it sits in HBM, so a
+    # fleet of ranks loads (or receives by broadcast) the blob instead of re-folding the 21 M-parameter checkpoint
+    _PACK_MAGIC = b"SMB200PK1"
+
+    def _pack_tag(self) -> bytes:
+        return ("%d,%d,%d,%d" % (self.search_size, self.precision, self.anchor_num, int(self.with_mask))).encode()
+
+    def save_packed(self, path: str):
+        blob = self.weight_blob()
+        torch.cuda.synchronize(self._device)
+        with open(path, "wb") as f:
+            tag = self._pack_tag()
+            f.write(self._PACK_MAGIC + len(tag).to_bytes(4, "little") + tag + blob.numel().to_bytes(8, "little"))
+            f.write(blob.cpu().numpy().tobytes())
+
+    def load_packed(self, path: str):
+        if not self._engine.value:
+            raise RuntimeError("call .to(cuda device) first")
+        with open(path, "rb") as f:
+            if f.read(len(self._PACK_MAGIC)) != self._PACK_MAGIC:
+                raise ValueError("not a siammask_b200 packed-weight file")
+            tag = f.read(int.from_bytes(f.read(4), "little"))
+            n = int.from_bytes(f.read(8), "little")
+            blob = self.weight_blob()
+            # the arena layout depends on anchor_num / with_mask only; precision and search size are recorded for
+            # information (both precisions read the same hi/lo planes)
+            if tag.split(b",")[2:] != self._pack_tag().split(b",")[2:] or n != blob.numel():
+                raise ValueError(f"packed weights were written for a different engine configuration ({tag!r})")
+            data = np.frombuffer(f.read(n), dtype=np.uint8)
+        blob.copy_(torch.from_numpy(data.copy()))
+        torch.cuda.synchronize(self._device)
+        self.adopt_weights()
+        return self
+
     # ------------------------------------------------------------------ the tracker-facing API
     def _prep(self, t: torch.Tensor, size: int) -> torch.Tensor:
         if not self._engine.value:

@@ -207,3 +207,25 @@ def test_host_buffer_path_sync_and_async(calib_sd):
         _lib.check(lib.sm_track_host_wait(m.handle, tickets[i]))
         for got, ref, n in zip(outs[i], want[i], ("cls", "loc", "refine")):
             assert_close(got, ref, 1e-6, f"async host path {n} step {i}")
+
+
+def test_packed_weight_file_roundtrip(calib_sd, tmp_path):
+    """save_packed / load_packed: an engine that never saw the checkpoint reproduces the packing engine bit for bit."""
+    z, x = synthetic_inputs(61, 1)
+    a = _engine(calib_sd)
+    path = str(tmp_path / "weights.smb")
+    a.save_packed(path)
+    b = smb.Custom(anchors=smb.DEFAULT_ANCHORS).eval().to("cuda")
+    with pytest.raises(RuntimeError):
+        b.template(z.cuda())                       # no weights yet: loud failure
+    b.load_packed(path)
+    outs = []
+    for m in (a, b):
+        m.template(z.cuda())
+        cls, loc, _ = m.track_mask(x.cuda(), mask_head=False)
+        outs.append((cls.clone(), loc.clone(), m.track_refine((7, 11)).clone()))
+    for u, v in zip(*outs):
+        assert torch.equal(u, v)
+    c = smb.Custom(anchors=smb.DEFAULT_ANCHORS, mask=False).eval().to("cuda")
+    with pytest.raises(ValueError):
+        c.load_packed(path)                        # RPN-only engine has a different arena layout
