@@ -43,7 +43,6 @@ constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 // BK = k-block width in fp16 elements: 64 (128-byte swizzled rows) or 32 (64-byte rows, finer pipeline stages)
 template <int BLOCK_N, int NSPLIT, int BK>
 struct Cfg {
-  static constexpr int BLOCK_K = BK;
   static constexpr int SWIZZLE = BK * 2;
   static constexpr int A_TILE_BYTES = BLOCK_M * BK * 2;
   static constexpr int B_TILE_BYTES = BLOCK_N * BK * 2;
@@ -605,7 +604,6 @@ void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, i
     }
     if (nsplit == 1) sg.tmA[1] = sg.tmA[0];
   }
-  bool ident = false;
   if (residual != nullptr) {
     // the residual rides the tensor pipe: needs the diag(2^e) block in the weights and 64-wide column blocks
     SMK_CHECK(res_col0 >= 0 && res_col0 % 64 == 0 && res_col0 + g0.Cout <= w_ld && block_n % 64 == 0,
@@ -622,7 +620,6 @@ void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, i
     for (int s = 0; s < nsplit; ++s)
       sg.tmA[s] = make_map_2d(s == 0 ? residual->hi : residual->lo, g0.Cout, (uint64_t)p.M, bk, BLOCK_M);
     if (nsplit == 1) sg.tmA[1] = sg.tmA[0];
-    ident = true;
     ep.res_hi = ep.res_lo = nullptr;       // accumulated by the MMA, not by the epilogue
   }
   if (p.nseg == 1) p.seg[1] = p.seg[0];
@@ -631,7 +628,6 @@ void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, i
   // NHWC split outputs go through smem + TMA stores; an epilogue-side residual (no diagonal block) needs the
   // direct path
   p.staged = (ep.out_mode == OUT_NHWC_SPLIT && block_n >= 32 && g0.Cout % 32 == 0 && ep.res_hi == nullptr) ? 1 : 0;
-  (void)ident;
   if (p.staged) {
     SMK_CHECK(nsplit == 1 || ep.out_lo != nullptr, "exact mode writes both planes");
     for (int s = 0; s < nsplit; ++s) p.tmOut[s] = make_map_epilogue(s == 0 ? ep.out_hi : ep.out_lo, g0.Cout, p.M);

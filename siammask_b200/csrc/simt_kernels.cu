@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) xcorr_nhwc_kernel(Act x, const __half* __
 // (b,c) plane.  Lane l owns input column j0+l; the KW-wide window is assembled with warp shuffles, so
 // every input element is read from memory exactly once per column pass; KH partial output rows are
 // carried in registers and retired as soon as their last input row has been consumed.
-template <int KH, int KW>
+template <int KH, int KW, int RB>
 __global__ void __launch_bounds__(256) xcorr_nchw_kernel(const float* __restrict__ x, const float* __restrict__ k,
                                                          float* __restrict__ out, int planes, int H, int W) {
   const int plane = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256) xcorr_nchw_kernel(const float* __restrict
     float acc[KH];
 #pragma unroll
     for (int u = 0; u < KH; ++u) acc[u] = 0.f;
-    constexpr int RB = 8;               // rows fetched per batch (memory-level parallelism)
+    // RB rows are fetched per batch before any of them is consumed (memory-level parallelism)
     for (int r0 = 0; r0 < H; r0 += RB) {
       float rowv[RB];
 #pragma unroll
@@ -705,7 +705,9 @@ void launch_xcorr_nchw_f32(const float* x, const float* k, float* out, int plane
   SMK_CHECK(H >= kh && W >= kw && planes > 0, "xcorr shapes");
   if (kh == 5 && kw == 5) {
     const int warps = 8;
-    xcorr_nchw_kernel<5, 5><<<(planes + warps - 1) / warps, warps * 32, 0, st>>>(x, k, out, planes, H, W);
+    // whole plane in flight when it has at most 32 rows (29 @255), two batches of 24 otherwise (45 @383)
+    if (H <= 32) xcorr_nchw_kernel<5, 5, 32><<<(planes + warps - 1) / warps, warps * 32, 0, st>>>(x, k, out, planes, H, W);
+    else xcorr_nchw_kernel<5, 5, 24><<<(planes + warps - 1) / warps, warps * 32, 0, st>>>(x, k, out, planes, H, W);
   } else {
     const size_t total = (size_t)planes * (H - kh + 1) * (W - kw + 1);
     xcorr_nchw_generic_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, k, out, planes, H, W, kh, kw);
