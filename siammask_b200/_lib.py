@@ -65,9 +65,15 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m siammask_b200.build` "
-            "(or __graft_entry__.build()). siammask_b200 has no fallback implementation.")
+        # a fresh checkout has sources only: compile the extension in-tree (nvcc, sm_100a) — there is no other
+        # implementation to fall back to, so a failed build is a hard error
+        try:
+            from . import build as _build
+            _build.build(force=True)
+        except Exception as exc:
+            raise ImportError(
+                f"{LIB_PATH} is missing and could not be built ({exc}); build it with "
+                "`python -m siammask_b200.build`. siammask_b200 has no fallback implementation.") from exc
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
