@@ -43,6 +43,8 @@ SIGNATURES = {
     "sm_track_host_wait": (C.c_int, [C.c_void_p, C.c_int32]),
     "sm_crop_resize": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                  C.c_void_p, C.c_void_p]),
+    "sm_warp_affine": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                 C.c_float, C.c_int32, C.c_void_p]),
     "sm_select": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 5 + [C.c_double, C.c_double] + [C.c_void_p] * 4),
     "sm_xcorr_depthwise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     "sm_conv2d": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 13 + [C.c_void_p]),

@@ -133,6 +133,8 @@ void launch_deconv(const float* p3, const float* w, const float* bias, float* ou
                    int cout, cudaStream_t st);
 void launch_split_to_f32(const Act& in, float* out, cudaStream_t st);
 void launch_import_nchw(const float* x_nchw, Act out, cudaStream_t st);
+void launch_warp_affine(const float* src, int sh, int sw, const double* maps, float* dst, int dh, int dw, float border,
+                        int B, cudaStream_t st);
 void launch_crop_resize(const uint8_t* frames, size_t frame_stride, int H, int W, const int32_t* box, int B, int model,
                         float* out, cudaStream_t st);
 void launch_select(const float* cls, const float* loc, const float* anchors, const float* window, const float* tsz,

@@ -1222,6 +1222,16 @@ int sm_crop_resize(const uint8_t* frames, size_t frame_stride, int32_t H, int32_
   SM_API_END
 }
 
+int sm_warp_affine(const float* src, int32_t src_h, int32_t src_w, const double* maps, float* dst, int32_t dst_h,
+                   int32_t dst_w, float border_value, int32_t B, void* stream) {
+  SM_API_BEGIN
+  SMK_CHECK(src && maps && dst && B >= 1 && src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0, "bad argument");
+  int ndev = 0;
+  SMK_CHECK(cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0, "no CUDA device: siammask_b200 has no CPU fallback");
+  smk::launch_warp_affine(src, src_h, src_w, maps, dst, dst_h, dst_w, border_value, B, static_cast<cudaStream_t>(stream));
+  SM_API_END
+}
+
 int sm_select(sm_engine* e, int32_t B, const float* cls, const float* loc, const float* anchors, const float* window,
               const float* target_sz_in_crop, double penalty_k, double window_influence, int32_t* best_idx, int32_t* pos,
               float* records, void* stream) {

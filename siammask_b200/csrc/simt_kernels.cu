@@ -650,6 +650,47 @@ __global__ void crop_resize_kernel(const uint8_t* __restrict__ frames, size_t fr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Mask paste-back: crop_back() of siamese_track (tools/test.py:263-282) = cv2.warpAffine(mask f32, M, (W,H),
+// INTER_LINEAR, BORDER_CONSTANT, borderValue) restated from OpenCV's imgwarp.cpp: M (forward map, double) is
+// inverted in double; source coordinates are generated in fixed point (AB_BITS = 10, 1/32-pixel sub-positions,
+// round_delta = 16); the four bilinear weights are float products of the 1-D (1 - f, f) tables; out-of-image taps
+// take the border value.  One thread per destination pixel; maps: double [B][6] on the device.
+__global__ void warp_affine_kernel(const float* __restrict__ src, int sh, int sw, const double* __restrict__ maps,
+                                   float* __restrict__ dst, int dh, int dw, float border) {
+  const int b = blockIdx.z;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= dw || y >= dh) return;
+  const double* m = maps + 6 * b;
+  double M0 = m[0], M1 = m[1], M2 = m[2], M3 = m[3], M4 = m[4], M5 = m[5];
+  double D = M0 * M4 - M1 * M3;
+  D = D != 0.0 ? 1.0 / D : 0.0;
+  const double A11 = M4 * D, A22 = M0 * D;
+  M0 = A11; M1 *= -D; M3 *= -D; M4 = A22;
+  const double b1 = -M0 * M2 - M1 * M5, b2 = -M3 * M2 - M4 * M5;
+  M2 = b1; M5 = b2;
+  const long long adelta = llrint(M0 * x * 1024.0), bdelta = llrint(M3 * x * 1024.0);
+  const long long X0 = llrint((M1 * y + M2) * 1024.0) + 16, Y0 = llrint((M4 * y + M5) * 1024.0) + 16;
+  const long long X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+  long long sx = X >> 5, sy = Y >> 5;
+  sx = sx < -32768 ? -32768 : (sx > 32767 ? 32767 : sx);     // saturate_cast<short>
+  sy = sy < -32768 ? -32768 : (sy > 32767 ? 32767 : sy);
+  const float fx = (float)(X & 31) / 32.f, fy = (float)(Y & 31) / 32.f;
+  const float wx0 = 1.f - fx, wy0 = 1.f - fy;
+  const float w00 = wy0 * wx0, w01 = wy0 * fx, w10 = fy * wx0, w11 = fy * fx;
+  const float* s = src + (size_t)b * sh * sw;
+  auto px = [&](long long yy, long long xx) -> float {
+    return (yy >= 0 && yy < sh && xx >= 0 && xx < sw) ? s[yy * sw + xx] : border;
+  };
+  // same evaluation order as remapBilinear (no fused multiply-add)
+  float v = __fmul_rn(px(sy, sx), w00);
+  v = __fadd_rn(v, __fmul_rn(px(sy, sx + 1), w01));
+  v = __fadd_rn(v, __fmul_rn(px(sy + 1, sx), w10));
+  v = __fadd_rn(v, __fmul_rn(px(sy + 1, sx + 1), w11));
+  dst[((size_t)b * dh + y) * dw + x] = v;
+}
+
 inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
   return (int)(g > 148 * 64 ? 148 * 64 : (g == 0 ? 1 : g));
@@ -746,6 +787,13 @@ void launch_split_to_f32(const Act& in, float* out, cudaStream_t st) {
 
 void launch_import_nchw(const float* x, Act out, cudaStream_t st) {
   import_nchw_kernel<<<grid_for(out.numel(), 256), 256, 0, st>>>(x, out);
+  SMK_CUDA(cudaGetLastError());
+}
+
+void launch_warp_affine(const float* src, int sh, int sw, const double* maps, float* dst, int dh, int dw, float border,
+                        int B, cudaStream_t st) {
+  dim3 block(32, 8), grid((dw + 31) / 32, (dh + 7) / 8, B);
+  warp_affine_kernel<<<grid, block, 0, st>>>(src, sh, sw, maps, dst, dh, dw, border);
   SMK_CUDA(cudaGetLastError());
 }
 

@@ -87,3 +87,25 @@ def crop_resize(frames: torch.Tensor, boxes, model_size: int) -> torch.Tensor:
         _lib.check(lib.sm_crop_resize(frames.data_ptr(), stride, H, W, full.data_ptr(), B, model_size, out.data_ptr(),
                                       _stream(dev)))
     return out
+
+
+def warp_affine(src: torch.Tensor, maps, dsize, border_value: float = -1.0) -> torch.Tensor:
+    """cv2.warpAffine(src, M, dsize, INTER_LINEAR, BORDER_CONSTANT, border_value) on the device (crop_back,
+    tools/test.py:263-275).  src f32 CUDA [h,w] or [B,h,w]; maps: forward 2x3 map(s); dsize = (width, height)."""
+    if not src.is_cuda:
+        raise RuntimeError("warp_affine expects a CUDA tensor; there is no CPU path")
+    lib = _lib.load()
+    dev = src.device
+    squeeze = src.dim() == 2
+    s3 = (src.unsqueeze(0) if squeeze else src).to(torch.float32).contiguous()
+    B, sh, sw = s3.shape
+    m = torch.as_tensor(maps, dtype=torch.float64).reshape(-1, 6)
+    if m.shape[0] != B:
+        raise ValueError("one 2x3 map per image expected")
+    m = m.to(dev).contiguous()
+    dw, dh = int(dsize[0]), int(dsize[1])
+    out = torch.empty(B, dh, dw, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        _lib.check(lib.sm_warp_affine(s3.data_ptr(), sh, sw, m.data_ptr(), out.data_ptr(), dh, dw, float(border_value), B,
+                                      _stream(dev)))
+    return out[0] if squeeze else out

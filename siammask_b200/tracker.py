@@ -5,7 +5,9 @@ and `track_refine` (tools/test.py:205-254) runs on the device (`Custom.select`, 
 host round trip per frame is 8 floats per stream; with any other `net` (e.g. the CPU oracle in the tests) the same
 arithmetic runs in numpy as in the reference.  Frames may be numpy arrays (crop + cv2.resize on the host, as in the
 reference, :67-110) or uint8 CUDA tensors (the crop + a bit-exact restatement of cv2's 8-bit INTER_LINEAR resize run on
-the device, `ops.crop_resize` / C ABI `sm_crop_resize`).  Mask paste-back (crop_back :263-282) stays on the host.
+the device, `ops.crop_resize` / C ABI `sm_crop_resize`).  Mask paste-back (crop_back :263-282) runs with cv2 on the
+host as in the reference, or on the device (`device_paste=True`, `ops.warp_affine` / `sm_warp_affine`); contour
+extraction and minAreaRect (:285-303) stay on the host.
 """
 from __future__ import annotations
 
@@ -195,8 +197,10 @@ def siamese_init(im, target_pos, target_sz, model, hp=None, device="cuda"):
     return state
 
 
-def siamese_track(state, im, mask_enable=False, refine_enable=False, device="cuda"):
-    """tools/test.py:172-315."""
+def siamese_track(state, im, mask_enable=False, refine_enable=False, device="cuda", device_paste=False):
+    """tools/test.py:172-315.  device_paste=True keeps the 127x127 mask on the GPU and pastes it back into the frame
+    with `ops.warp_affine` (bit-exact restatement of the cv2.warpAffine in crop_back); only the thresholded uint8 mask
+    travels to the host for the contour / minAreaRect step."""
     p, net = state["p"], state["net"]
     avg_chans, window = state["avg_chans"], state["window"]
     target_pos, target_sz = state["target_pos"], state["target_sz"]
@@ -241,14 +245,20 @@ def siamese_track(state, im, mask_enable=False, refine_enable=False, device="cud
         _, delta_y, delta_x = np.unravel_index(best_id, (p.anchor_num, p.score_size, p.score_size))
         if refine_enable:
             m = net.track_refine(pos_dev if pos_dev is not None else (delta_y, delta_x))
-            m = m.sigmoid().squeeze().view(p.out_size, p.out_size).cpu().data.numpy()
+            m = m.sigmoid().squeeze().view(p.out_size, p.out_size)
         else:
-            m = mask[0, :, delta_y, delta_x].sigmoid().squeeze().view(p.out_size, p.out_size).cpu().data.numpy()
+            m = mask[0, :, delta_y, delta_x].sigmoid().squeeze().view(p.out_size, p.out_size)
+        on_dev = device_paste and m.is_cuda
+        if not on_dev:
+            m = m.cpu().data.numpy()
 
         def crop_back(image, bbox, out_sz, padding=-1):          # tools/test.py:263-275
             a = (out_sz[0] - 1) / bbox[2]
             b = (out_sz[1] - 1) / bbox[3]
             mapping = np.array([[a, 0, -a * bbox[0]], [0, b, -b * bbox[1]]]).astype(float)
+            if on_dev:
+                from .ops import warp_affine
+                return warp_affine(image, mapping, (out_sz[0], out_sz[1]), padding)
             return cv2.warpAffine(image, mapping, (out_sz[0], out_sz[1]), flags=cv2.INTER_LINEAR,
                                   borderMode=cv2.BORDER_CONSTANT, borderValue=padding)
 
@@ -259,7 +269,10 @@ def siamese_track(state, im, mask_enable=False, refine_enable=False, device="cud
         s = p.out_size / sub_box[2]
         back_box = [-sub_box[0] * s, -sub_box[1] * s, state["im_w"] * s, state["im_h"] * s]
         mask_in_img = crop_back(m, back_box, (state["im_w"], state["im_h"]))
-        target_mask = (mask_in_img > p.seg_thr).astype(np.uint8)
+        if on_dev:
+            target_mask = (mask_in_img > p.seg_thr).to(torch.uint8).cpu().numpy()
+        else:
+            target_mask = (mask_in_img > p.seg_thr).astype(np.uint8)
         contours = cv2.findContours(target_mask, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE)[-2]
         cnt_area = [cv2.contourArea(cnt) for cnt in contours]
         if len(contours) != 0 and np.max(cnt_area) > 100:

@@ -70,3 +70,60 @@ def test_loop_with_device_frames_equals_host_frames(calib_sd):
             pos.append(st["target_pos"].copy())
         traj.append(np.asarray(pos))
     np.testing.assert_array_equal(traj[0], traj[1])
+
+
+def _random_maps(rng, n):
+    maps = []
+    for _ in range(n):
+        a, b = 0.3 + rng.rand() * 2.5, 0.3 + rng.rand() * 2.5
+        maps.append(np.array([[a, 0, -rng.rand() * 120 + 20], [0, b, -rng.rand() * 90 + 15]], dtype=float))
+    return maps
+
+
+def test_warp_restatement_is_bit_exact():
+    from oracle.cv_warp import warp_affine_f32
+    rng = np.random.RandomState(11)
+    for M in _random_maps(rng, 4):
+        src = rng.rand(127, 127).astype(np.float32)
+        ref = cv2.warpAffine(src, M, (320, 240), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=-1)
+        assert np.array_equal(ref, warp_affine_f32(src, M, (320, 240)))
+
+
+@pytest.mark.gpu
+def test_device_paste_back_matches_cv2():
+    """crop_back (tools/test.py:263-282) on the device == cv2.warpAffine, bit for bit."""
+    from siammask_b200.ops import warp_affine
+    rng = np.random.RandomState(12)
+    maps = _random_maps(rng, 5)
+    srcs = rng.rand(5, 127, 127).astype(np.float32)
+    out = warp_affine(torch.from_numpy(srcs).cuda(), np.stack(maps), (854, 480)).cpu().numpy()
+    for i, M in enumerate(maps):
+        ref = cv2.warpAffine(srcs[i], M, (854, 480), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=-1)
+        assert np.array_equal(out[i], ref), f"map {i}: max diff {np.abs(out[i] - ref).max()}"
+
+
+@pytest.mark.gpu
+def test_loop_with_device_paste_back(calib_sd):
+    """Whole loop with device crop + device select + device paste-back == the same loop with host cv2 steps."""
+    import siammask_b200 as smb
+    from oracle.synthetic_video import make_frames
+    frames, boxes = make_frames()
+    x, y, w, h = boxes[0]
+    hp = {"instance_size": 255, "base_size": 8, "out_size": 127, "seg_thr": 0.35, "penalty_k": 0.04,
+          "window_influence": 0.4, "lr": 1.0}
+    res = []
+    for dev_path in (False, True):
+        m = smb.Custom(anchors=smb.DEFAULT_ANCHORS).load_state_dict(calib_sd).eval().to("cuda")
+        fs = [torch.from_numpy(f).cuda() for f in frames] if dev_path else frames
+        st = tracker.siamese_init(fs[0], np.array([x + w / 2, y + h / 2]), np.array([w, h]), m, hp, device="cuda")
+        rec = []
+        for f in fs[1:]:
+            st = tracker.siamese_track(st, f, mask_enable=True, refine_enable=True, device="cuda", device_paste=dev_path)
+            mk = st["mask"]
+            mk = mk.cpu().numpy() if isinstance(mk, torch.Tensor) else mk
+            rec.append((st["target_pos"].copy(), mk.copy(), np.asarray(st["ploygon"]).copy()))
+        res.append(rec)
+    for (p0, m0, g0), (p1, m1, g1) in zip(*res):
+        np.testing.assert_array_equal(p0, p1)
+        np.testing.assert_array_equal(m0, m1)
+        np.testing.assert_allclose(g0, g1, atol=1e-4)
