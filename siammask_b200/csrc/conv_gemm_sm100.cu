@@ -13,8 +13,9 @@
 //   weights as hi+lo fp16 pairs (22 significant bits) and issues three MMAs per k-step
 //   (hi*hi into one TMEM accumulator, lo*hi + hi*lo into a second one, summed in the epilogue) — fp32-class
 //   results from the fp16 tensor pipe.
-// * Epilogue (4 warps, one TMEM lane quarter each): acc*alpha[c]+beta[c] (+residual) (ReLU) written as
-//   NHWC split-fp16 planes, NHWC fp32, or NCHW fp32 (the boundary layout of the reference's outputs,
+// * Epilogue (8 warps, two per TMEM lane quarter, alternating 32-column chunks): tcgen05.ld -> acc*alpha[c]+beta[c]
+//   (ReLU) -> NHWC split-fp16 planes through 64B-swizzled smem and TMA stores (direct stores would touch 32
+//   sectors per request), or NHWC fp32, or NCHW fp32 (the boundary layout of the reference's outputs,
 //   tools/test.py:205-206) — TMEM lanes are pixels, so NCHW stores are coalesced across the warp.
 //
 // * K may consist of up to two SEGMENTS that accumulate into the same tile: (conv over input 0) + (conv over
