@@ -21,15 +21,6 @@ __device__ __forceinline__ void split_store(__half* hi, __half* lo, size_t i, fl
   hi[i] = h;
   if (lo != nullptr) lo[i] = __float2half_rn(v - __half2float(h));
 }
-__device__ __forceinline__ float2 split_load2(const __half* hi, const __half* lo, size_t i) {
-  float2 v = __half22float2(*reinterpret_cast<const __half2*>(hi + i));
-  if (lo != nullptr) {
-    const float2 l = __half22float2(*reinterpret_cast<const __half2*>(lo + i));
-    v.x += l.x;
-    v.y += l.y;
-  }
-  return v;
-}
 __device__ __forceinline__ void split_store2(__half* hi, __half* lo, size_t i, float2 v) {
   const __half2 h = __floats2half2_rn(v.x, v.y);
   *reinterpret_cast<__half2*>(hi + i) = h;
@@ -691,6 +682,94 @@ __global__ void warp_affine_kernel(const float* __restrict__ src, int sh, int sw
   dst[((size_t)b * dh + y) * dw + x] = v;
 }
 
+// Tiled variant for the 16/32-channel layers (h2, post0, h1): a persistent block stages the weights once, then
+// walks 8x16 output tiles: the (upsampled, summed) input halo of a tile is built in shared memory once, every thread
+// computes 2 horizontally adjacent pixels x CPT output channels out of smem.  Rows are padded to CIN+1 floats so
+// the 8 pixel pairs of a warp hit distinct banks; the COUT/CPT threads of a pair read the same input (broadcast).
+constexpr int SCT_H = 8, SCT_W = 16;
+template <int CIN, int COUT, int CPT>
+__global__ void __launch_bounds__((SCT_H * SCT_W / 2) * (COUT / CPT))
+small_conv3x3_tiled_kernel(const float* __restrict__ a, const float* __restrict__ b2, int B, int Hi, int Wi, int Ho, int Wo,
+                           const int* __restrict__ ymap, const int* __restrict__ xmap, const float* __restrict__ w,
+                           const float* __restrict__ bias, int relu, float* __restrict__ out) {
+  constexpr int G = COUT / CPT;
+  constexpr int NT = (SCT_H * SCT_W / 2) * G;
+  constexpr int ROW = CIN + 1;                                   // padded pixel pitch (floats)
+  constexpr int HALO_H = SCT_H + 2, HALO_W = SCT_W + 2;
+  extern __shared__ __align__(16) float smem_sc[];
+  float* sw = smem_sc;                                           // [9][CIN][COUT]
+  float* sin = smem_sc + 9 * CIN * COUT;                         // [HALO_H][HALO_W][ROW]
+  for (int i = threadIdx.x; i < 9 * CIN * COUT; i += NT) sw[i] = w[i];
+  const int tiles_x = (Wo + SCT_W - 1) / SCT_W, tiles_y = (Ho + SCT_H - 1) / SCT_H;
+  const int num_tiles = B * tiles_y * tiles_x;
+  const int g = threadIdx.x % G;
+  const int pp = threadIdx.x / G;
+  const int py = pp / (SCT_W / 2), px0 = (pp % (SCT_W / 2)) * 2;
+  const int co0 = g * CPT;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+    const int y0 = ty * SCT_H - 1, x0 = tx * SCT_W - 1;         // halo origin in output coordinates
+    __syncthreads();                                             // previous tile's readers are done (and sw is visible)
+    for (int i = threadIdx.x; i < HALO_H * HALO_W * (CIN / 4); i += NT) {
+      const int c4 = (i % (CIN / 4)) * 4;
+      const int hp = i / (CIN / 4);
+      const int hy = hp / HALO_W, hx = hp % HALO_W;
+      const int y = y0 + hy, x = x0 + hx;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (y >= 0 && y < Ho && x >= 0 && x < Wo) {
+        const size_t src = (((size_t)b * Hi + ymap[y]) * Wi + xmap[x]) * CIN + c4;
+        v = *reinterpret_cast<const float4*>(a + src);
+        if (b2 != nullptr) {
+          const float4 v2 = *reinterpret_cast<const float4*>(b2 + src);
+          v.x += v2.x; v.y += v2.y; v.z += v2.z; v.w += v2.w;
+        }
+      }
+      float* d = sin + (size_t)hp * ROW + c4;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    __syncthreads();
+    float acc0[CPT], acc1[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) { acc0[j] = bias[co0 + j]; acc1[j] = acc0[j]; }
+#pragma unroll 1
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll 1
+      for (int s = 0; s < 3; ++s) {
+        const float* in0 = sin + ((size_t)(py + r) * HALO_W + px0 + s) * ROW;
+        const float* in1 = in0 + ROW;
+        const float* wt = sw + (r * 3 + s) * CIN * COUT + co0;
+#pragma unroll 8
+        for (int c = 0; c < CIN; ++c) {
+          const float a0 = in0[c], a1 = in1[c];
+#pragma unroll
+          for (int j = 0; j < CPT; j += 4) {
+            const float4 wv = *reinterpret_cast<const float4*>(wt + c * COUT + j);
+            acc0[j + 0] = fmaf(a0, wv.x, acc0[j + 0]); acc1[j + 0] = fmaf(a1, wv.x, acc1[j + 0]);
+            acc0[j + 1] = fmaf(a0, wv.y, acc0[j + 1]); acc1[j + 1] = fmaf(a1, wv.y, acc1[j + 1]);
+            acc0[j + 2] = fmaf(a0, wv.z, acc0[j + 2]); acc1[j + 2] = fmaf(a1, wv.z, acc1[j + 2]);
+            acc0[j + 3] = fmaf(a0, wv.w, acc0[j + 3]); acc1[j + 3] = fmaf(a1, wv.w, acc1[j + 3]);
+          }
+        }
+      }
+    }
+    const int oy = ty * SCT_H + py;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int ox = tx * SCT_W + px0 + k;
+      if (oy < Ho && ox < Wo) {
+        const float* acc = k == 0 ? acc0 : acc1;
+        float* dst = out + (((size_t)b * Ho + oy) * Wo + ox) * COUT + co0;
+#pragma unroll
+        for (int j = 0; j < CPT; j += 4) {
+          float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+          if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          *reinterpret_cast<float4*>(dst + j) = o;
+        }
+      }
+    }
+  }
+}
+
 inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
   return (int)(g > 148 * 64 ? 148 * 64 : (g == 0 ? 1 : g));
@@ -837,7 +916,21 @@ void launch_small_conv3x3_maps(const float* a, const float* b, int B, int Hi, in
     launched = true;                                                                                             \
   }
   bool launched = false;
-  SMK_SC(32, 32, 8) SMK_SC(32, 16, 4) SMK_SC(16, 16, 4) SMK_SC(16, 4, 4) SMK_SC(4, 4, 4) SMK_SC(4, 1, 1)
+#define SMK_SCT(CI, CO, CPT)                                                                                     \
+  if (Cin == CI && Cout == CO) {                                                                                 \
+    constexpr int NT = (SCT_H * SCT_W / 2) * (CO / CPT);                                                         \
+    constexpr int SMEM = (9 * CI * CO + (SCT_H + 2) * (SCT_W + 2) * (CI + 1)) * (int)sizeof(float);              \
+    static unsigned long long attr = 0;                                                                          \
+    ensure_dynamic_smem(small_conv3x3_tiled_kernel<CI, CO, CPT>, SMEM, attr);                                    \
+    const int tiles = B * ((Ho + SCT_H - 1) / SCT_H) * ((Wo + SCT_W - 1) / SCT_W);                               \
+    const int blocks = tiles < 148 * 2 ? tiles : 148 * 2;                                                        \
+    small_conv3x3_tiled_kernel<CI, CO, CPT><<<blocks, NT, SMEM, st>>>(a, b, B, Hi, Wi, Ho, Wo, ymap, xmap, w,    \
+                                                                       bias, relu, out);                         \
+    launched = true;                                                                                             \
+  }
+  SMK_SCT(32, 32, 8) SMK_SCT(32, 16, 4) SMK_SCT(16, 16, 4)
+#undef SMK_SCT
+  if (!launched) { SMK_SC(16, 4, 4) SMK_SC(4, 4, 4) SMK_SC(4, 1, 1) }
   SMK_CHECK(launched, "small conv: unsupported (Cin, Cout)");
 #undef SMK_SC
   SMK_CUDA(cudaGetLastError());
