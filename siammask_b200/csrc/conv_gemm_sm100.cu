@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
             float* dst = ep.out_f32 + (static_cast<size_t>(b) * p.Cout + n) * HoWo + hw;
 #pragma unroll
             for (int j = 0; j < CH; ++j)
-              if (n + j < p.Cout) dst[static_cast<size_t>(j) * HoWo] = v[j];
+              if (n + j < p.Cout) __stcs(dst + static_cast<size_t>(j) * HoWo, v[j]);   // write-once output: stream past L2
           }
         }
       }
