@@ -61,6 +61,7 @@ struct GemmParams {
   int M, Cout, Ho, Wo;
   int n_tiles, m_tiles;
   int staged;           // 1: epilogue goes smem -> TMA store (NHWC split outputs)
+  int reverse_m;        // 1: walk the M tiles from the last to the first (see Engine::conv_into: L2 reuse)
   Epilogue ep;
 };
 
@@ -110,7 +111,7 @@ void launch_gemm_conv(const Act& in, const ConvGeom& g, const __half* w_hi, cons
 // diag(2^e) block starts at weight column res_col0 (< 0: none).  w_ld = row length of the weight matrix.
 void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, int res_col0, const __half* w_hi,
                        const __half* w_lo, int cout_pad, int w_ld, const Epilogue& ep, int nsplit, int num_sms,
-                       cudaStream_t st);
+                       cudaStream_t st, bool reverse_m = false);
 
 // stem_sm100.cu : 7x7/2 stem on the tensor cores (weights [64][192] K-major, k = (r*7+s)*3+c, pow2-scaled)
 void launch_stem_tc(const float* x_nchw, int B, int S, const __half* w_hi, const __half* w_lo, const float* alpha,

@@ -79,6 +79,13 @@ __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CH])
   else tmem_ld_32x32b_x16(taddr, r);
 }
 
+// tile -> M block.  With reverse_m the persistent CTAs walk the M tiles from the end: a layer then starts on the rows
+// its producer wrote last, which are the ones still resident in the 126 MB L2 (activations of 250 MB stream through).
+__device__ __forceinline__ int m_block(const GemmParams& p, int tile) {
+  const int mb = tile / p.n_tiles;
+  return p.reverse_m ? p.m_tiles - 1 - mb : mb;
+}
+
 template <int BLOCK_N, int NSPLIT, int BK>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BLOCK_N, NSPLIT, BK>;
@@ -132,7 +139,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.n_tiles) * BLOCK_M;
+      const int m0 = m_block(p, tile) * BLOCK_M;
       const int n0 = (tile % p.n_tiles) * BLOCK_N;
       const int q = m0 % p.Wo;
       const int t = m0 / p.Wo;
@@ -247,7 +254,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
           const int acc = it % C::ACC_STAGES;
           const uint32_t acc_phase = (it / C::ACC_STAGES) & 1;
-          const int m0 = (tile / p.n_tiles) * BLOCK_M + quarter * 32;
+          const int m0 = m_block(p, tile) * BLOCK_M + quarter * 32;
           const int n0 = (tile % p.n_tiles) * BLOCK_N;
           mbar_wait(&tfull_bar[acc], acc_phase);
           tcgen05_fence_after();
@@ -317,7 +324,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
     for (int tile = blockIdx.x; it >= 0 && tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it % C::ACC_STAGES;
       const uint32_t acc_phase = (it / C::ACC_STAGES) & 1;
-      const int m0 = (tile / p.n_tiles) * BLOCK_M;
+      const int m0 = m_block(p, tile) * BLOCK_M;
       const int n0 = (tile % p.n_tiles) * BLOCK_N;
       const int m = m0 + quarter * 32 + lane;
       const bool row_ok = m < p.M;
@@ -558,7 +565,7 @@ void launch_gemm_conv(const Act& in, const ConvGeom& g, const __half* w_hi, cons
 
 void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, int res_col0, const __half* w_hi,
                        const __half* w_lo, int cout_pad, int w_ld, const Epilogue& ep_in, int nsplit, int num_sms,
-                       cudaStream_t st) {
+                       cudaStream_t st, bool reverse_m) {
   SMK_CHECK(nconv >= 1 && nconv <= 2, "1 or 2 convolution segments");
   SMK_CHECK(nconv + (residual != nullptr ? 1 : 0) <= 2, "at most two K segments");
   Epilogue ep = ep_in;
@@ -580,6 +587,7 @@ void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, i
   if (ep.out_mode != OUT_NCHW_F32) SMK_CHECK(g0.Cout == cout_pad, "NHWC outputs need Cout to match the padded tile width");
   p.n_tiles = cout_pad / block_n;
   p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  p.reverse_m = reverse_m ? 1 : 0;
   p.nseg = 0;
   for (int i = 0; i < nconv; ++i) {
     const ConvGeom& g = convs[i].g;
