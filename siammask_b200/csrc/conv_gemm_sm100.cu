@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace smk {
@@ -577,11 +578,20 @@ void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, i
   p.Cout = g0.Cout;
   p.Ho = Ho;
   p.Wo = Wo;
-  // Tile choice: 128 x 128 (exact: two TMEM accumulators per tile, double buffered) or 128 x 256 (fast).
-  // A 128 x 256 exact tile (32-wide k-blocks, single accumulator stage: conv_gemm_kernel<256, 2, 32>) was measured on
-  // B200 and is NOT faster (layer3.0 fused conv 1.33 vs 1.36 ms, layer3 conv2 0.203 vs 0.183 ms): both shapes sit
-  // at the ~65 % tensor-pipe duty cycle that cuBLAS itself sustains on this part (MEASURED_PEAKS.json).
-  const int block_n = cout_pad < 256 ? cout_pad : (nsplit == 2 ? 128 : 256);
+  // Tile choice.  fast: 128 x 256.  exact: 128 x 128 with two double-buffered TMEM accumulator pairs, or — when the
+  // main loop is long enough to amortise a non-overlapped epilogue (>= 24 k-blocks) — 128 x 256 with a single
+  // accumulator stage and two 96 KB ring stages.  The SM's shared-memory port (128 B/clk) carries both the TMA fills
+  // and the operand reads of every tcgen05.mma; per k-block a 128 x 128 exact tile moves 64 KB in + 96 KB out of smem
+  // for 768 MMA-clocks (208 B/clk -> <= 61 % tensor duty, 63-66 % measured), the 128 x 256 tile 96 + 144 KB for 1536
+  // (156 B/clk -> <= 82 %).  Measured on B200 (profiles/r01_tile_ab.md): layer3.0 conv3+downsample 1.45 -> 1.16 ms,
+  // 3x3 convs -10..-17 %, short-K 1x1 layers +8..+35 % slower (they stay on 128 x 128).  32-wide k-blocks (64 B
+  // rows) were slower everywhere.  SMB200_EXACT_N256: 0 = never wide, 1 = default rule, 3 = always wide.
+  static const int n256 = [] { const char* e = getenv("SMB200_EXACT_N256"); return e ? atoi(e) : 1; }();
+  int total_kb = residual != nullptr ? 2 : 0;
+  for (int i = 0; i < nconv; ++i) total_kb += convs[i].g.KH * convs[i].g.KW * convs[i].g.Cin / 64;
+  const bool wide_exact = nsplit == 2 && cout_pad >= 256 && ep.out_mode == OUT_NHWC_SPLIT &&
+                          (n256 == 3 || (n256 == 1 && total_kb >= 24));
+  const int block_n = cout_pad < 256 ? cout_pad : (nsplit == 2 && !wide_exact ? 128 : 256);
   const int bk = 64;
   SMK_CHECK(cout_pad % block_n == 0, "cout_pad must be a multiple of the N tile");
   if (ep.out_mode != OUT_NCHW_F32) SMK_CHECK(g0.Cout == cout_pad, "NHWC outputs need Cout to match the padded tile width");
@@ -657,8 +667,8 @@ void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, i
     SMK_DISPATCH(64)
     SMK_DISPATCH(128)
     case 256:
-      SMK_CHECK(nsplit == 1, "exact mode uses N tiles <= 128");
-      launch_cfg<256, 1>(p, num_sms, st);
+      if (nsplit == 1) launch_cfg<256, 1>(p, num_sms, st);
+      else launch_cfg<256, 2, 64>(p, num_sms, st);
       break;
     default: SMK_CHECK(false, "unsupported N tile");
   }
