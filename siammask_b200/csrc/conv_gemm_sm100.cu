@@ -43,11 +43,14 @@ constexpr int NUM_EPI_WARPS = 8;   // two per TMEM lane quarter, alternating 32-
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
 // BK = k-block width in fp16 elements: 64 (128-byte swizzled rows) or 32 (64-byte rows, finer pipeline stages)
-template <int BLOCK_N, int NSPLIT, int BK>
+// CG = CTAs per tile: 1, or 2 = a CTA pair (cluster of 2, tcgen05 cta_group::2) computing a 256 x BLOCK_N tile — each
+// CTA stages its own 128 A rows and HALF of the B rows, so smem fill and MMA operand reads per flop drop by a third.
+template <int BLOCK_N, int NSPLIT, int BK, int CG = 1>
 struct Cfg {
   static constexpr int SWIZZLE = BK * 2;
   static constexpr int A_TILE_BYTES = BLOCK_M * BK * 2;
-  static constexpr int B_TILE_BYTES = BLOCK_N * BK * 2;
+  static constexpr int B_ROWS = BLOCK_N / CG;           // B rows staged by one CTA
+  static constexpr int B_TILE_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = NSPLIT * (A_TILE_BYTES + B_TILE_BYTES);
   // epilogue staging: 8 warps x NSPLIT planes x (32 rows x 64 B)
   static constexpr int STG_TILE_BYTES = 32 * 64;
@@ -71,6 +74,7 @@ struct Cfg {
   static constexpr int SMEM_BYTES = SMEM_BYTES_RAW < 120 * 1024 ? 120 * 1024 : SMEM_BYTES_RAW;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N constraint for M=128");
+  static_assert(CG == 1 || (CG == 2 && BLOCK_N >= 64 && B_ROWS % 8 == 0), "CTA pairs: N >= 64");
   static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget");
 };
 
@@ -82,14 +86,18 @@ __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CH])
 
 // tile -> M block.  With reverse_m the persistent CTAs walk the M tiles from the end: a layer then starts on the rows
 // its producer wrote last, which are the ones still resident in the 126 MB L2 (activations of 250 MB stream through).
-__device__ __forceinline__ int m_block(const GemmParams& p, int tile) {
+// With CTA pairs a tile covers CG consecutive M blocks; `rank` picks this CTA's.  The result may be == m_tiles for
+// the odd last block of a pair (the caller clamps its loads and skips its stores).
+template <int CG>
+__device__ __forceinline__ int m_block(const GemmParams& p, int tile, int rank) {
+  const int groups = (p.m_tiles + CG - 1) / CG;
   const int mb = tile / p.n_tiles;
-  return p.reverse_m ? p.m_tiles - 1 - mb : mb;
+  return (p.reverse_m ? groups - 1 - mb : mb) * CG + rank;
 }
 
-template <int BLOCK_N, int NSPLIT, int BK>
+template <int BLOCK_N, int NSPLIT, int BK, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg<BLOCK_N, NSPLIT, BK>;
+  using C = Cfg<BLOCK_N, NSPLIT, BK, CG>;
   constexpr int STAGES = C::STAGES;
   constexpr int CH = C::CH;
   constexpr int BLOCK_K = BK;
@@ -106,7 +114,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;   // position in the CTA pair; 0 = leader
+  const int num_tiles = ((p.m_tiles + CG - 1) / CG) * p.n_tiles;
+  const int tile0 = blockIdx.x / CG;
+  const int tile_step = gridDim.x / CG;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSPLIT; ++i) {
@@ -119,7 +130,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], NUM_EPI_WARPS);   // one arrival per epilogue warp
+      mbar_init(&tempty_bar[a], CG * NUM_EPI_WARPS);   // one arrival per epilogue warp (of both CTAs of a pair)
     }
     if (p.staged)
       for (int i = 0; i < NSPLIT; ++i) tma_prefetch_desc(&p.tmOut[i]);
@@ -128,20 +139,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
   }
   if (warp == 1) {
     __syncwarp();
-    tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    if constexpr (CG == 2) tmem_alloc_pair<C::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<C::TMEM_COLS>(tmem_slot);
   }
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();      // the peer's barriers are initialised before anything signals them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (threadIdx.x == 0) {
     // ===================== TMA producer =====================
+    // CTA pairs: both producers fill their own smem but signal the LEADER's full barrier, which expects the bytes of
+    // both CTAs; each waits on its own empty barrier (the leader's tcgen05.commit is multicast to the pair).
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = m_block(p, tile) * BLOCK_M;
+    const uint32_t full0 = CG == 2 ? mapa_shared(smem_u32(&full_bar[0]), 0) : 0;
+    auto acquire = [&](uint32_t bytes_per_cta) {
+      if constexpr (CG == 2) mbar_wait_guarded(&empty_bar[stage], phase ^ 1);
+      else mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CG * bytes_per_cta);
+    };
+    auto load_2d = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
+      if constexpr (CG == 2) tma_load_2d_pair(dst, map, full0 + stage * 8, c0, c1);
+      else tma_load_2d(dst, map, &full_bar[stage], c0, c1);
+    };
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      const int mb = m_block<CG>(p, tile, rank);
+      const int m0 = (mb < p.m_tiles ? mb : p.m_tiles - 1) * BLOCK_M;   // odd last block of a pair: reload, never stored
       const int n0 = (tile % p.n_tiles) * BLOCK_N;
+      const int nb0 = n0 + rank * C::B_ROWS;                            // first B row this CTA stages
       const int q = m0 % p.Wo;
       const int t = m0 / p.Wo;
       const int pq = t % p.Ho;
@@ -152,13 +179,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
           // identity segment: A = residual tile [128 rows x 64 cols] (K-major), B = diag(2^e) block (hi plane only)
 #pragma unroll 1
           for (int kb = 0; kb < BLOCK_N / BLOCK_K; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            acquire(NSPLIT * A_TILE_BYTES + C::B_TILE_BYTES);
             uint8_t* st = smem + stage * C::STAGE_BYTES;
-            mbar_arrive_expect_tx(&full_bar[stage], NSPLIT * A_TILE_BYTES + C::B_TILE_BYTES);
 #pragma unroll
-            for (int s = 0; s < NSPLIT; ++s)
-              tma_load_2d(st + s * A_TILE_BYTES, &sg.tmA[s], &full_bar[stage], n0 + kb * BLOCK_K, m0);
-            tma_load_2d(st + NSPLIT * A_TILE_BYTES, &p.tmB[0], &full_bar[stage], sg.b_col0 + n0 + kb * BLOCK_K, n0);
+            for (int s = 0; s < NSPLIT; ++s) load_2d(st + s * A_TILE_BYTES, &sg.tmA[s], n0 + kb * BLOCK_K, m0);
+            load_2d(st + NSPLIT * A_TILE_BYTES, &p.tmB[0], sg.b_col0 + n0 + kb * BLOCK_K, nb0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           continue;
@@ -167,39 +192,61 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
         const int hb = pq * sg.stride - sg.pad;
 #pragma unroll 1
         for (int kb = 0; kb < sg.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          acquire(C::STAGE_BYTES);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           const int tap = kb / sg.cblks;
           const int c0 = (kb - tap * sg.cblks) * BLOCK_K;
 #pragma unroll
           for (int s = 0; s < NSPLIT; ++s) {
             uint8_t* a_dst = st + s * A_TILE_BYTES;
             if (sg.mode == 0) {
-              tma_load_2d(a_dst, &sg.tmA[s], &full_bar[stage], c0, m0);
+              load_2d(a_dst, &sg.tmA[s], c0, m0);
             } else {
               const int r = tap / sg.KW;
               const int sx = tap - r * sg.KW;
-              tma_load_im2col_4d(a_dst, &sg.tmA[s], &full_bar[stage], c0, wb, hb, nb,
-                                 static_cast<uint16_t>(sx * sg.dil), static_cast<uint16_t>(r * sg.dil));
+              if constexpr (CG == 2)
+                tma_load_im2col_4d_pair(a_dst, &sg.tmA[s], full0 + stage * 8, c0, wb, hb, nb,
+                                        static_cast<uint16_t>(sx * sg.dil), static_cast<uint16_t>(r * sg.dil));
+              else
+                tma_load_im2col_4d(a_dst, &sg.tmA[s], &full_bar[stage], c0, wb, hb, nb,
+                                   static_cast<uint16_t>(sx * sg.dil), static_cast<uint16_t>(r * sg.dil));
             }
             uint8_t* b_dst = st + NSPLIT * A_TILE_BYTES + s * C::B_TILE_BYTES;
-            tma_load_2d(b_dst, &p.tmB[s], &full_bar[stage], sg.b_col0 + kb * BLOCK_K, n0);
+            load_2d(b_dst, &p.tmB[s], sg.b_col0 + kb * BLOCK_K, nb0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (threadIdx.x == 32) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_f16(BLOCK_M, BLOCK_N);
+    if constexpr (CG == 2) {
+      // tail: every multicast commit aimed at this CTA's empty barriers has landed before it may exit
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_wait_guarded(&empty_bar[stage], phase ^ 1);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (threadIdx.x == 32 && rank == 0) {
+    // ===================== MMA issuer (pairs: the leader CTA issues for both) =====================
+    constexpr uint32_t idesc = umma_idesc_f16(BLOCK_M * CG, BLOCK_N);
+    auto wait_bar = [&](uint64_t* bar, uint32_t parity) {
+      if constexpr (CG == 2) mbar_wait_guarded(bar, parity);
+      else mbar_wait(bar, parity);
+    };
+    auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t accumulate) {
+      if constexpr (CG == 2) umma_f16_pair(d, da, db, idesc, accumulate);
+      else umma_f16(d, da, db, idesc, accumulate);
+    };
+    auto commit = [&](uint64_t* bar) {
+      if constexpr (CG == 2) umma_commit_pair(bar);
+      else umma_commit(bar);
+    };
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const int acc = it % C::ACC_STAGES;
       const uint32_t acc_phase = (it / C::ACC_STAGES) & 1;
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      wait_bar(&tempty_bar[acc], acc_phase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * C::ACC_COLS;
       uint32_t acc_main = 0, acc_lo = 0;     // 0 on the first MMA into each accumulator of this tile
@@ -210,7 +257,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
         const bool last_seg = sgi == p.nseg - 1;
 #pragma unroll 1
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          wait_bar(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t b_hi = a_hi + NSPLIT * A_TILE_BYTES;
@@ -219,20 +266,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
             const uint32_t koff = k * UMMA_K * 2;   // bytes along K inside the 128B swizzle row
             const uint64_t da_hi = umma_desc_kmajor<C::SWIZZLE>(a_hi + koff);
             const uint64_t db_hi = umma_desc_kmajor<C::SWIZZLE>(b_hi + koff);
-            umma_f16(tmem_d, da_hi, db_hi, idesc, acc_main);
+            mma(tmem_d, da_hi, db_hi, acc_main);
             acc_main = 1;
             if constexpr (NSPLIT == 2) {
               const uint64_t da_lo = umma_desc_kmajor<C::SWIZZLE>(a_hi + A_TILE_BYTES + koff);
-              umma_f16(tmem_d + BLOCK_N, da_lo, db_hi, idesc, acc_lo);
+              mma(tmem_d + BLOCK_N, da_lo, db_hi, acc_lo);
               acc_lo = 1;
               if (!ident) {
                 const uint64_t db_lo = umma_desc_kmajor<C::SWIZZLE>(b_hi + C::B_TILE_BYTES + koff);
-                umma_f16(tmem_d + BLOCK_N, da_hi, db_lo, idesc, 1u);
+                mma(tmem_d + BLOCK_N, da_hi, db_lo, 1u);
               }
             }
           }
-          umma_commit(&empty_bar[stage]);                                   // smem slot free once these MMAs retire
-          if (last_seg && kb == nkb - 1) umma_commit(&tfull_bar[acc]);      // accumulator complete
+          commit(&empty_bar[stage]);                                   // smem slot free once these MMAs retire
+          if (last_seg && kb == nkb - 1) commit(&tfull_bar[acc]);      // accumulator complete
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -244,6 +291,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
     const Epilogue& ep = p.ep;
     const int HoWo = p.Ho * p.Wo;
     int it = 0;
+    // pairs: the accumulator stage is released to the LEADER's MMA thread by the epilogue warps of both CTAs
+    const uint32_t tempty0 = CG == 2 ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0;
+    auto wait_acc = [&](uint64_t* bar, uint32_t parity) {
+      if constexpr (CG == 2) mbar_wait_guarded(bar, parity);
+      else mbar_wait(bar, parity);
+    };
+    auto release_acc = [&](int acc) {
+      if constexpr (CG == 2) mbar_arrive_cluster(tempty0 + acc * 8);
+      else mbar_arrive(&tempty_bar[acc]);
+    };
     if constexpr (BLOCK_N >= 32) {
       if (p.staged) {
         // ---- staged path: TMEM -> registers -> 64B-swizzled smem -> TMA store.  Two warps share each block of 32
@@ -252,16 +309,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
         uint8_t* buf = stg_base + (warp - 2) * C::STG_WARP_BYTES;
         constexpr int CHUNKS = BLOCK_N / 32;
         const int swz = (lane >> 1) & 3;                       // Swizzle<2,4,3>: 16B chunk ^= (row >> 1) & 3
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
           const int acc = it % C::ACC_STAGES;
           const uint32_t acc_phase = (it / C::ACC_STAGES) & 1;
-          const int m0 = m_block(p, tile) * BLOCK_M + quarter * 32;
+          const int mb = m_block<CG>(p, tile, rank);
+          const int m0 = mb * BLOCK_M + quarter * 32;
           const int n0 = (tile % p.n_tiles) * BLOCK_N;
-          mbar_wait(&tfull_bar[acc], acc_phase);
+          wait_acc(&tfull_bar[acc], acc_phase);
           tcgen05_fence_after();
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * C::ACC_COLS;
 #pragma unroll 1
-          for (int c = half; c < CHUNKS; c += 2) {
+          for (int c = (mb < p.m_tiles ? half : CHUNKS); c < CHUNKS; c += 2) {
             uint32_t r[32];
             tmem_ld_chunk<32>(taddr + c * 32, r);
             if constexpr (NSPLIT == 2) {
@@ -316,20 +374,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
           }
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) release_acc(acc);
         }
         if (lane == 0) tma_store_wait_all();
         it = -1;   // tiles consumed
       }
     }
-    for (int tile = blockIdx.x; it >= 0 && tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; it >= 0 && tile < num_tiles; tile += tile_step, ++it) {
       const int acc = it % C::ACC_STAGES;
       const uint32_t acc_phase = (it / C::ACC_STAGES) & 1;
-      const int m0 = m_block(p, tile) * BLOCK_M;
+      const int m0 = m_block<CG>(p, tile, rank) * BLOCK_M;
       const int n0 = (tile % p.n_tiles) * BLOCK_N;
       const int m = m0 + quarter * 32 + lane;
       const bool row_ok = m < p.M;
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      wait_acc(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * C::ACC_COLS;
 #pragma unroll 1
@@ -419,16 +477,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) release_acc(acc);
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // both CTAs are done with the pair's TMEM and with signalling each other
   if (warp == 1) {
     __syncwarp();
     tcgen05_fence_after();
-    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    if constexpr (CG == 2) tmem_dealloc_pair<C::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -517,15 +577,32 @@ CUtensorMap make_map_im2col(const __half* base, const Act& in, const ConvGeom& g
   return m;
 }
 
-template <int BLOCK_N, int NSPLIT, int BK = 64>
+template <int BLOCK_N, int NSPLIT, int BK = 64, int CG = 1>
 void launch_cfg(const GemmParams& p, int num_sms, cudaStream_t st) {
-  using C = Cfg<BLOCK_N, NSPLIT, BK>;
-  auto kern = conv_gemm_kernel<BLOCK_N, NSPLIT, BK>;
+  using C = Cfg<BLOCK_N, NSPLIT, BK, CG>;
+  auto kern = conv_gemm_kernel<BLOCK_N, NSPLIT, BK, CG>;
   static unsigned long long attr_done = 0;
   ensure_dynamic_smem(kern, C::SMEM_BYTES, attr_done);
-  const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);
+  const int tiles = ((p.m_tiles + CG - 1) / CG) * p.n_tiles;
+  const int slots = num_sms / CG;                      // one CTA (pair) per SM (pair)
+  const int grid = (tiles < slots ? tiles : slots) * CG;
+  if constexpr (CG == 1) {
+    kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = CG;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    SMK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  }
   SMK_CUDA(cudaGetLastError());
 }
 
@@ -593,6 +670,16 @@ void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, i
                           (n256 == 3 || (n256 == 1 && total_kb >= 24));
   const int block_n = cout_pad < 256 ? cout_pad : (nsplit == 2 && !wide_exact ? 128 : 256);
   const int bk = 64;
+  // CTA pairs (cluster of 2, tcgen05 cta_group::2, 256 x 256 tiles): each CTA stages its own 128 A rows and half of
+  // the B rows, so fills and operand reads through the smem port drop by a third (104 B/clk for the exact tile).
+  // Measured (profiles/r01_tile_ab.md): exact long-K layers -4..-9 %; fast mode +5..+12 % slower (not smem-bound:
+  // stays single-CTA); 256 x 128 pairs on the short-K exact layers are neutral to slower (lock-step epilogues).
+  // SMB200_CTA_PAIR: 0 = never, 1 = default rule (exact 256-wide tiles), 2 = also the exact 128-wide tiles,
+  // 3 = also the fast 256-wide tiles.
+  static const int pair_mode = [] { const char* e = getenv("SMB200_CTA_PAIR"); return e ? atoi(e) : 1; }();
+  const int cg = (pair_mode >= 1 && wide_exact) || (pair_mode >= 2 && block_n == 128 && nsplit == 2) ||
+                         (pair_mode >= 3 && block_n == 256)
+                     ? 2 : 1;
   SMK_CHECK(cout_pad % block_n == 0, "cout_pad must be a multiple of the N tile");
   if (ep.out_mode != OUT_NCHW_F32) SMK_CHECK(g0.Cout == cout_pad, "NHWC outputs need Cout to match the padded tile width");
   p.n_tiles = cout_pad / block_n;
@@ -642,7 +729,8 @@ void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, i
     ep.res_hi = ep.res_lo = nullptr;       // accumulated by the MMA, not by the epilogue
   }
   if (p.nseg == 1) p.seg[1] = p.seg[0];
-  for (int s = 0; s < nsplit; ++s) p.tmB[s] = make_map_2d(s == 0 ? w_hi : w_lo, (uint64_t)w_ld, cout_pad, bk, block_n);
+  for (int s = 0; s < nsplit; ++s)
+    p.tmB[s] = make_map_2d(s == 0 ? w_hi : w_lo, (uint64_t)w_ld, cout_pad, bk, block_n / cg);
   if (nsplit == 1) p.tmB[1] = p.tmB[0];
   // NHWC split outputs go through smem + TMA stores; an epilogue-side residual (no diagonal block) needs the
   // direct path
@@ -665,9 +753,15 @@ void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, i
     SMK_DISPATCH(16)
     SMK_DISPATCH(32)
     SMK_DISPATCH(64)
-    SMK_DISPATCH(128)
+    case 128:
+      if (nsplit == 2 && cg == 2) launch_cfg<128, 2, 64, 2>(p, num_sms, st);
+      else if (nsplit == 2) launch_cfg<128, 2>(p, num_sms, st);
+      else launch_cfg<128, 1>(p, num_sms, st);
+      break;
     case 256:
-      if (nsplit == 1) launch_cfg<256, 1>(p, num_sms, st);
+      if (nsplit == 1 && cg == 2) launch_cfg<256, 1, 64, 2>(p, num_sms, st);
+      else if (nsplit == 1) launch_cfg<256, 1>(p, num_sms, st);
+      else if (cg == 2) launch_cfg<256, 2, 64, 2>(p, num_sms, st);
       else launch_cfg<256, 2, 64>(p, num_sms, st);
       break;
     default: SMK_CHECK(false, "unsupported N tile");

@@ -75,6 +75,18 @@ struct Arena {
   }
 };
 
+// One execution lane: its own workspace, stream set and cached per-step tensors.  A batch of >= kLaneMinB streams
+// is split over two lanes that run concurrently (streams are independent): the persistent GEMM kernels of one lane
+// fill the SMs the other lane's kernels leave idle in their last wave and in the low-occupancy refine tail.
+struct Lane {
+  Arena search, refine;
+  std::map<std::string, Act> named;            // p0, p1, p2, search, corr_* of the lane's last track
+  cudaStream_t own = nullptr;                  // lane 1 only: its main stream (lane 0 runs on the caller's stream)
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+  int cap_B = 0;                               // largest batch this lane's arenas were sized for
+};
+constexpr int kLaneMinB = 16;
+
 }  // namespace
 
 class Engine {
@@ -151,7 +163,11 @@ class Engine {
   size_t blob_bytes_ = 0;
   bool weights_ready_ = false;
 
-  Arena search_arena_, templ_arena_, refine_arena_;
+  Arena templ_arena_;
+  Lane lanes_[2];
+  Lane* cur_ = &lanes_[0];             // lane whose schedule is being enqueued
+  int n_lanes_ = 1;                    // 2 when max_batch >= kLaneMinB (SMB200_LANES=1 disables)
+  int split_n_ = 1, split_B0_ = 0;     // how the last track divided its batch
   // per-slot template caches: [branch][slot][5][5][256] split planes, and zf for export
   __half* kcache_hi_ = nullptr;
   __half* kcache_lo_ = nullptr;
@@ -171,7 +187,8 @@ class Engine {
   std::map<int, const int*> maps_;
 
   // state of the last track (Custom.feature / .search / .corr_feature, custom.py:182-184)
-  std::map<std::string, Act> named_;
+  Act zf_;                             // template feature of the last sm_template (export)
+  bool have_zf_ = false;
   int last_B_ = 0;
   bool have_mask_feats_ = false;
 
@@ -194,7 +211,8 @@ class Engine {
   struct GraphEntry {
     int seen = 0;
     cudaGraphExec_t exec = nullptr;
-    std::map<std::string, Act> named;
+    std::map<std::string, Act> named[2];
+    int split_n = 1, split_B0 = 0;
     int last_B = 0;
     bool have_mask_feats = false;
     int64_t launches = 0;
@@ -202,14 +220,21 @@ class Engine {
   bool use_graphs_ = false;
   std::map<std::vector<uint64_t>, GraphEntry> graphs_;
   void track_impl(int slot0, int B, const float* x, float* cls, float* loc, float* mask, int flags, cudaStream_t st);
+  void track_lane(int slot0, int B, const float* x, float* cls, float* loc, float* mask, int flags, cudaStream_t st);
   void refine_impl(int B, const int32_t* pos, float* out, cudaStream_t st);
+  void refine_lane(int B, const int32_t* pos, float* out, cudaStream_t st);
+  bool defer_join_ = false;            // host-buffer path: lane 1 stays forked between its track and its refine
+  bool lane1_forked_ = false;
   template <typename F>
   void run_with_graph(const std::vector<uint64_t>& key, cudaStream_t st, F&& body) {
     if (!use_graphs_ || profiling_) { body(); return; }
     GraphEntry& ge = graphs_[key];
     if (ge.exec != nullptr) {
       SMK_CUDA(cudaGraphLaunch(ge.exec, st));
-      for (auto& kv : ge.named) if (kv.first != "zf") named_[kv.first] = kv.second;
+      for (int l = 0; l < 2; ++l)
+        for (auto& kv : ge.named[l]) lanes_[l].named[kv.first] = kv.second;
+      split_n_ = ge.split_n;
+      split_B0_ = ge.split_B0;
       last_B_ = ge.last_B;
       have_mask_feats_ = ge.have_mask_feats;
       launches_ += ge.launches;
@@ -229,7 +254,9 @@ class Engine {
     SMK_CUDA(cudaStreamEndCapture(st, &graph));
     SMK_CUDA(cudaGraphInstantiate(&ge.exec, graph, 0));
     SMK_CUDA(cudaGraphDestroy(graph));
-    ge.named = named_;
+    for (int l = 0; l < 2; ++l) ge.named[l] = lanes_[l].named;
+    ge.split_n = split_n_;
+    ge.split_B0 = split_B0_;
     ge.last_B = last_B_;
     ge.have_mask_feats = have_mask_feats_;
     ge.launches = launches_ - l0;
@@ -239,7 +266,6 @@ class Engine {
   // independent sub-graphs (the three correlation heads; the refine stage's v-branches) run on auxiliary
   // streams forked from / joined back into the caller's stream with events
   static constexpr int kAux = 3;
-  cudaStream_t aux_[kAux] = {nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> sync_events_;
   size_t sync_next_ = 0;
   cudaEvent_t next_sync_event() {
@@ -421,14 +447,25 @@ Engine::Engine(const sm_config& cfg) : cfg_(cfg), exact_(cfg.precision == SM_PRE
   }
 
   // workspace sizes: dry-run the schedule with a measuring arena
-  search_arena_.cap = measure_arena(cfg.max_batch, cfg.search_size, true);
+  {
+    const char* e = std::getenv("SMB200_LANES");
+    n_lanes_ = (cfg.max_batch >= kLaneMinB && !(e != nullptr && atoi(e) == 1)) ? 2 : 1;
+  }
+  lanes_[0].cap_B = n_lanes_ == 2 ? std::max((cfg.max_batch + 1) / 2, std::min(cfg.max_batch, kLaneMinB - 1)) : cfg.max_batch;
+  lanes_[1].cap_B = n_lanes_ == 2 ? cfg.max_batch / 2 : 0;
   templ_arena_.cap = measure_arena(cfg.max_batch, 127, false);
-  SMK_CUDA(cudaMalloc(&search_arena_.base, search_arena_.cap));
   SMK_CUDA(cudaMalloc(&templ_arena_.base, templ_arena_.cap));
-  if (cfg_.with_mask) {
-    // refine stage: crops + conv outputs, ~ (61*61*64 + 31*31*(256+64) + 15*15*(512+128)) split + fp32 maps
-    refine_arena_.cap = align_up((size_t)cfg.max_batch * 6u * 1024 * 1024 + (1u << 20));
-    SMK_CUDA(cudaMalloc(&refine_arena_.base, refine_arena_.cap));
+  for (int l = 0; l < n_lanes_; ++l) {
+    Lane& ln = lanes_[l];
+    ln.search.cap = measure_arena(ln.cap_B, cfg.search_size, true);
+    SMK_CUDA(cudaMalloc(&ln.search.base, ln.search.cap));
+    if (cfg_.with_mask) {
+      // refine stage: crops + conv outputs, ~ (61*61*64 + 31*31*(256+64) + 15*15*(512+128)) split + fp32 maps
+      ln.refine.cap = align_up((size_t)ln.cap_B * 6u * 1024 * 1024 + (1u << 20));
+      SMK_CUDA(cudaMalloc(&ln.refine.base, ln.refine.cap));
+    }
+    for (int i = 0; i < kAux; ++i) SMK_CUDA(cudaStreamCreateWithFlags(&ln.aux[i], cudaStreamNonBlocking));
+    if (l == 1) SMK_CUDA(cudaStreamCreateWithFlags(&ln.own, cudaStreamNonBlocking));
   }
   const size_t kc = (size_t)n_branches_ * cfg.num_slots * 25 * 256;
   SMK_CUDA(cudaMalloc(&kcache_hi_, kc * sizeof(__half)));
@@ -462,19 +499,23 @@ Engine::Engine(const sm_config& cfg) : cfg_(cfg), exact_(cfg.precision == SM_PRE
   SMK_CUDA(cudaMalloc(&maps_dev_, all.size() * sizeof(int)));
   SMK_CUDA(cudaMemcpy(maps_dev_, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice));
   for (int i = 0; i < 6; ++i) maps_[pairs[i][0] * 1000 + pairs[i][1]] = maps_dev_ + offs[i];
-  for (int i = 0; i < kAux; ++i) SMK_CUDA(cudaStreamCreateWithFlags(&aux_[i], cudaStreamNonBlocking));
-  sync_events_.resize(32);
+  sync_events_.resize(64);
   for (auto& e : sync_events_) SMK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
-  total_bytes_ = blob_bytes_ + search_arena_.cap + templ_arena_.cap + refine_arena_.cap + 2 * kc * sizeof(__half) +
+  total_bytes_ = blob_bytes_ + templ_arena_.cap + lanes_[0].search.cap + lanes_[0].refine.cap + lanes_[1].search.cap +
+                 lanes_[1].refine.cap + 2 * kc * sizeof(__half) +
                  2 * (B * 3 * S * S + B * 6 * A * R_ * R_ + B * 127 * 127) * sizeof(float);
 }
 
 Engine::~Engine() {
   cudaFree(blob_);
-  cudaFree(search_arena_.base);
   cudaFree(templ_arena_.base);
-  cudaFree(refine_arena_.base);
+  for (auto& ln : lanes_) {
+    cudaFree(ln.search.base);
+    cudaFree(ln.refine.base);
+    for (int i = 0; i < kAux; ++i) if (ln.aux[i]) cudaStreamDestroy(ln.aux[i]);
+    if (ln.own) cudaStreamDestroy(ln.own);
+  }
   cudaFree(kcache_hi_);
   cudaFree(kcache_lo_);
   for (int i = 0; i < 2; ++i) {
@@ -486,7 +527,6 @@ Engine::~Engine() {
   if (h2d_stream_) cudaStreamDestroy(h2d_stream_);
   if (d2h_stream_) cudaStreamDestroy(d2h_stream_);
   cudaFree(maps_dev_);
-  for (int i = 0; i < kAux; ++i) if (aux_[i]) cudaStreamDestroy(aux_[i]);
   for (auto e : sync_events_) cudaEventDestroy(e);
   for (auto e : event_pool_) cudaEventDestroy(e);
   for (auto& kv : graphs_) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -506,7 +546,7 @@ size_t Engine::measure_arena(int B, int S, bool search) {
     }
   }
   measuring_ = false;
-  named_.clear();
+  cur_->named.clear();
   return align_up(ar.peak + (1u << 20));
 }
 
@@ -766,7 +806,7 @@ Act Engine::backbone(const float* x, int B, int S, Arena& ar, bool keep, cudaStr
   }
   last_end_[p0.hi] = +1;       // stem and pool write front to back
   last_end_[y.hi] = +1;
-  if (keep) named_["p0"] = p0;
+  if (keep) cur_->named["p0"] = p0;
   const char* names[3] = {"layer1", "layer2", "layer3"};
   const int blocks[3] = {3, 4, 6};
   for (int l = 0; l < 3; ++l) {
@@ -783,7 +823,7 @@ Act Engine::backbone(const float* x, int B, int S, Arena& ar, bool keep, cudaStr
         y = conv(t2, c3, true, &res, ar, st);
       }
     }
-    if (keep) named_[std::string("p") + std::to_string(l + 1)] = y;
+    if (keep) cur_->named[std::string("p") + std::to_string(l + 1)] = y;
   }
   Act xf = conv(y, L("features.downsample.downsample.0"), false, nullptr, ar, st);
   if (xf.W < 20) {   // custom.py:21-24
@@ -803,7 +843,8 @@ void Engine::do_template(int slot0, int B, const float* z, cudaStream_t st) {
   templ_arena_.reset();
   Act zf = backbone(z, B, 127, templ_arena_, false, st);
   SMK_CHECK(zf.H == 7 && zf.W == 7, "template feature must be 7x7");
-  named_["zf"] = zf;
+  zf_ = zf;
+  have_zf_ = true;
   for (int br = 0; br < n_branches_; ++br) {
     const ConvW& ck = L(std::string(kBranch[br]) + "conv_kernel.0");
     Epilogue ep;
@@ -832,24 +873,47 @@ void Engine::track_impl(int slot0, int B, const float* x, float* cls, float* loc
   const bool want_mask_head = (flags & SM_TRACK_MASK_HEAD) != 0;
   SMK_CHECK(!(want_feats || want_mask_head) || cfg_.with_mask, "engine was built without the mask branch");
   SMK_CHECK(!want_mask_head || mask != nullptr, "mask output buffer required");
-  search_arena_.reset();
-  Act zf_keep;
-  bool had_zf = named_.count("zf") > 0;
-  if (had_zf) zf_keep = named_["zf"];
-  named_.clear();
-  if (had_zf) named_["zf"] = zf_keep;
-  Act xf = backbone(x, B, cfg_.search_size, search_arena_, true, st);
-  named_["search"] = xf;
+  // split the streams over the two lanes; lane 1 forks from / joins back into the caller's stream
+  const int nl = (n_lanes_ == 2 && B >= kLaneMinB) ? 2 : 1;
+  const int B0 = nl == 2 ? (B + 1) / 2 : B;
+  SMK_CHECK(B0 <= lanes_[0].cap_B && B - B0 <= lanes_[1].cap_B, "lane workspace too small for this batch");
+  split_n_ = nl;
+  split_B0_ = B0;
+  const size_t S = cfg_.search_size, A = cfg_.anchor_num, RR = (size_t)R_ * R_;
+  // fork before anything of this call is enqueued on `st`, so the lanes really run side by side
+  if (nl == 2 && concurrent() && !lane1_forked_) { order_after(st, lanes_[1].own); lane1_forked_ = true; }
+  for (int l = nl - 1; l >= 0; --l) {
+    cur_ = &lanes_[l];
+    const int b0 = l == 0 ? 0 : B0, nbat = l == 0 ? B0 : B - B0;
+    cudaStream_t ls = (l == 0 || !concurrent()) ? st : lanes_[1].own;
+    track_lane(slot0 + b0, nbat, x + b0 * 3 * S * S, cls + b0 * 2 * A * RR, loc + b0 * 4 * A * RR,
+               mask != nullptr ? mask + (size_t)b0 * 63 * 63 * RR : nullptr, flags, ls);
+  }
+  cur_ = &lanes_[0];
+  if (lane1_forked_ && !defer_join_) { order_after(lanes_[1].own, st); lane1_forked_ = false; }
+  last_B_ = B;
+  have_mask_feats_ = want_feats || want_mask_head;
+}
+
+void Engine::track_lane(int slot0, int B, const float* x, float* cls, float* loc, float* mask, int flags,
+                        cudaStream_t st) {
+  const bool want_feats = (flags & SM_TRACK_MASK_FEATURES) != 0;
+  const bool want_mask_head = (flags & SM_TRACK_MASK_HEAD) != 0;
+  Arena& search_arena = cur_->search;
+  search_arena.reset();
+  cur_->named.clear();
+  Act xf = backbone(x, B, cfg_.search_size, search_arena, true, st);
+  cur_->named["search"] = xf;
   const int nb = (want_feats || want_mask_head) ? 3 : 2;
   float* outs[3] = {cls, loc, mask};
   for (int br = 0; br < nb; ++br) {
     // the branches only share their input: run them side by side (their 1x1 heads and the xcorr do not fill
     // the GPU on their own)
-    cudaStream_t bs = (concurrent() && br > 0) ? aux_[br - 1] : st;
+    cudaStream_t bs = (concurrent() && br > 0) ? cur_->aux[br - 1] : st;
     order_after(st, bs);
     const std::string P = kBranch[br];
-    Act cs = conv(xf, L(P + "conv_search.0"), true, nullptr, search_arena_, bs);
-    Act corr = alloc_act(search_arena_, B, cs.H - 4, cs.W - 4, 256);
+    Act cs = conv(xf, L(P + "conv_search.0"), true, nullptr, search_arena, bs);
+    Act corr = alloc_act(search_arena, B, cs.H - 4, cs.W - 4, 256);
     const size_t off = ((size_t)br * cfg_.num_slots + slot0) * 25 * 256;
     {
       Scope sc(this, std::string(kCorrName[br]), "xcorr", 2.0 * 25 * corr.numel(),
@@ -858,9 +922,9 @@ void Engine::track_impl(int slot0, int B, const float* x, float* cls, float* loc
       ++launches_;
       last_end_[corr.hi] = +1;
     }
-    named_[kCorrName[br]] = corr;
+    cur_->named[kCorrName[br]] = corr;
     if (!(br == 2 && !want_mask_head)) {
-      Act h = conv(corr, L(P + "head.0"), true, nullptr, search_arena_, bs);
+      Act h = conv(corr, L(P + "head.0"), true, nullptr, search_arena, bs);
       Epilogue ep;
       ep.relu = 0;
       ep.out_mode = OUT_NCHW_F32;
@@ -868,9 +932,7 @@ void Engine::track_impl(int slot0, int B, const float* x, float* cls, float* loc
       conv_into(h, L(P + "head.3"), ep, bs);
     }
   }
-  for (int br = 1; br < nb; ++br) order_after((concurrent()) ? aux_[br - 1] : st, st);
-  last_B_ = B;
-  have_mask_feats_ = want_feats || want_mask_head;
+  for (int br = 1; br < nb; ++br) order_after((concurrent()) ? cur_->aux[br - 1] : st, st);
 }
 
 F32T Engine::small(const F32T& a, const F32T* b, int Ho, const ConvW& Lw, bool relu, float* out_override, Arena& ar,
@@ -893,23 +955,37 @@ F32T Engine::small(const F32T& a, const F32T* b, int Ho, const ConvW& Lw, bool r
 void Engine::do_refine(int B, const int32_t* pos, float* out, cudaStream_t st) {
   SMK_CHECK(have_mask_feats_ && B == last_B_, "sm_refine must follow sm_track(..., SM_TRACK_MASK_FEATURES) with the same B");
   const std::vector<uint64_t> key = {2, (uint64_t)B, (uint64_t)pos, (uint64_t)out, (uint64_t)st,
-                                     (uint64_t)named_["p0"].hi};
+                                     (uint64_t)lanes_[0].named["p0"].hi};
   run_with_graph(key, st, [&] { refine_impl(B, pos, out, st); });
 }
 
 void Engine::refine_impl(int B, const int32_t* pos, float* out, cudaStream_t st) {
   SMK_CHECK(cfg_.with_mask, "engine was built without the mask branch");
   SMK_CHECK(have_mask_feats_ && B == last_B_, "sm_refine must follow sm_track(..., SM_TRACK_MASK_FEATURES) with the same B");
-  Arena& ar = refine_arena_;
+  // same split as the track that cached the features
+  if (split_n_ == 2 && concurrent() && !lane1_forked_) { order_after(st, lanes_[1].own); lane1_forked_ = true; }
+  for (int l = split_n_ - 1; l >= 0; --l) {
+    cur_ = &lanes_[l];
+    const int b0 = l == 0 ? 0 : split_B0_, nbat = l == 0 ? split_B0_ : B - split_B0_;
+    cudaStream_t ls = (l == 0 || !concurrent()) ? st : lanes_[1].own;
+    refine_lane(nbat, pos + 2 * b0, out + (size_t)b0 * 127 * 127, ls);
+  }
+  cur_ = &lanes_[0];
+  if (lane1_forked_) { order_after(lanes_[1].own, st); lane1_forked_ = false; }
+}
+
+void Engine::refine_lane(int B, const int32_t* pos, float* out, cudaStream_t st) {
+  Arena& ar = cur_->refine;
   ar.reset();
   const std::string R = "refine_model.";
-  const Act& p0 = named_["p0"];
-  const Act& p1 = named_["p1"];
-  const Act& p2 = named_["p2"];
-  const Act& corr = named_["corr_mask"];
+  const Act& p0 = cur_->named["p0"];
+  const Act& p1 = cur_->named["p1"];
+  const Act& p2 = cur_->named["p2"];
+  const Act& corr = cur_->named["corr_mask"];
   // The three v-branches (crop -> conv -> conv on p2 / p1 / p0) depend only on the cached pyramid: they run on
   // auxiliary streams while the main stream walks deconv -> h2 -> post0 -> h1 -> post1 -> h0 -> post2.
-  cudaStream_t s2 = concurrent() ? aux_[0] : st, s1 = concurrent() ? aux_[1] : st, s0 = concurrent() ? aux_[2] : st;
+  cudaStream_t s2 = concurrent() ? cur_->aux[0] : st, s1 = concurrent() ? cur_->aux[1] : st,
+               s0 = concurrent() ? cur_->aux[2] : st;
   order_after(st, s2);
   order_after(st, s1);
   order_after(st, s0);
@@ -978,7 +1054,15 @@ int Engine::track_host_async(int slot0, int B, const float* xh, float* clsh, flo
     SMK_CUDA(cudaMemcpyAsync(stage_pos_[t], posh, (size_t)B * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, h2d_stream_));
   SMK_CUDA(cudaEventRecord(h2d_done_[t], h2d_stream_));
   SMK_CUDA(cudaStreamWaitEvent(st, h2d_done_[t], 0));
-  do_track(slot0, B, stage_x_[t], stage_cls_[t], stage_loc_[t], nullptr, refine ? SM_TRACK_MASK_FEATURES : 0, st);
+  // lane 1 stays forked between its track and its refine (nobody reads cls/loc on `st` in between)
+  defer_join_ = refine && !use_graphs_;
+  try {
+    do_track(slot0, B, stage_x_[t], stage_cls_[t], stage_loc_[t], nullptr, refine ? SM_TRACK_MASK_FEATURES : 0, st);
+  } catch (...) {
+    defer_join_ = false;
+    throw;
+  }
+  defer_join_ = false;
   if (refine) do_refine(B, stage_pos_[t], stage_mask_[t], st);
   SMK_CUDA(cudaEventRecord(compute_done_[t], st));
   SMK_CUDA(cudaStreamWaitEvent(d2h_stream_, compute_done_[t], 0));
@@ -1004,11 +1088,22 @@ void Engine::track_host(int slot0, int B, const float* xh, float* clsh, float* l
 }
 
 void Engine::do_export(const char* what, float* out, int64_t* shape4, cudaStream_t st) {
-  auto it = named_.find(what);
-  SMK_CHECK(it != named_.end(), std::string("no cached tensor named '") + what + "'");
-  const Act& a = it->second;
-  if (shape4 != nullptr) { shape4[0] = a.B; shape4[1] = a.C; shape4[2] = a.H; shape4[3] = a.W; }
-  if (out != nullptr) { launch_split_to_f32(a, out, st); ++launches_; }
+  if (std::string(what) == "zf") {
+    SMK_CHECK(have_zf_, "no cached tensor named 'zf'");
+    if (shape4 != nullptr) { shape4[0] = zf_.B; shape4[1] = zf_.C; shape4[2] = zf_.H; shape4[3] = zf_.W; }
+    if (out != nullptr) { launch_split_to_f32(zf_, out, st); ++launches_; }
+    return;
+  }
+  int total_B = 0;
+  for (int l = 0; l < split_n_; ++l) {       // the lanes hold consecutive blocks of streams
+    auto it = lanes_[l].named.find(what);
+    SMK_CHECK(it != lanes_[l].named.end(), std::string("no cached tensor named '") + what + "'");
+    const Act& a = it->second;
+    if (shape4 != nullptr) { shape4[1] = a.C; shape4[2] = a.H; shape4[3] = a.W; }
+    if (out != nullptr) { launch_split_to_f32(a, out + (size_t)total_B * a.C * a.H * a.W, st); ++launches_; }
+    total_B += a.B;
+  }
+  if (shape4 != nullptr) shape4[0] = total_B;
 }
 
 std::string Engine::profile_dump() {

@@ -84,6 +84,69 @@ def test_batched_streams_and_slots(calib_sd):
     assert float((cls2[1] - cls[1]).abs().max()) > 1e-3
 
 
+def test_two_lane_batch_matches_single_stream_runs(calib_sd):
+    """B=17 (>= 16) is split 9 + 8 over the engine's two concurrent lanes: every stream must equal its own
+    single-stream run (B=1 engine = one lane, already pinned to the oracle), intermediates are gathered across the
+    lanes, the graph-replay and host-buffer paths (lane 1 stays forked between track and refine) agree."""
+    import ctypes as C
+    from siammask_b200 import _lib
+    B = 17
+    z, x = synthetic_inputs(71, B)
+    _, x2 = synthetic_inputs(72, B)
+    pos = torch.tensor([[(3 * b) % 25, (7 * b + 2) % 25] for b in range(B)], dtype=torch.int32)
+    m = _engine(calib_sd, max_batch=B, num_slots=B)
+    m.template(z.cuda())
+    cls, loc, mask = m.track_mask(x.cuda())
+    p2 = m.export("p2")
+    ref = m.track_refine(pos.cuda())
+    assert p2.shape[0] == B
+    one = _engine(calib_sd)
+    o = Oracle(calib_sd)
+    for b in (0, 8, 9, 16):                                  # last of lane 0, first / last of lane 1
+        one.template(z[b:b + 1].cuda())
+        c1, l1, m1 = one.track_mask(x[b:b + 1].cuda())
+        assert_close(cls[b:b + 1], c1, 1e-6, f"cls stream {b}")
+        assert_close(loc[b:b + 1], l1, 1e-6, f"loc stream {b}")
+        assert_close(mask[b:b + 1], m1, 1e-6, f"mask stream {b}")
+        assert_close(p2[b:b + 1], one.export("p2"), 1e-6, f"p2 stream {b}")
+        assert_close(ref[b:b + 1], one.track_refine(tuple(int(v) for v in pos[b])), 1e-6, f"refine stream {b}")
+    o.template(z[9:10])
+    ocls, oloc, _ = o.track_mask(x[9:10], with_mask_head=False)
+    assert_close(cls[9:10], ocls, TOL, "cls stream 9 vs oracle")
+    assert_close(ref[9:10], o.track_refine(tuple(int(v) for v in pos[9])), TOL, "refine stream 9 vs oracle")
+    # graph replay with both lanes captured
+    g = _engine(calib_sd, max_batch=B, num_slots=B, graphs=True)
+    g.template(z.cuda())
+    for it, xin in enumerate([x, x2, x]):
+        ce, le, _ = m.track_mask(xin.cuda(), mask_head=False)
+        re_ = m.track_refine(pos.cuda())
+        cg, lg, _ = g.track_mask(xin.cuda(), mask_head=False)
+        rg = g.track_refine(pos.cuda())
+        assert_close(cg, ce, 1e-6, f"two-lane graph cls call {it}")
+        assert_close(rg, re_, 1e-6, f"two-lane graph refine call {it}")
+    # host-buffer pipeline
+    lib = _lib.load()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    want = []
+    for xin in (x, x2):
+        c, l, _ = m.track_mask(xin.cuda(), mask_head=False)
+        want.append((c.cpu(), l.cpu(), m.track_refine(pos.cuda()).cpu()))
+    xs = [x.contiguous().pin_memory(), x2.contiguous().pin_memory()]
+    outs = [(torch.empty(B, 10, 25, 25).pin_memory(), torch.empty(B, 20, 25, 25).pin_memory(),
+             torch.empty(B, 127 * 127).pin_memory()) for _ in range(2)]
+    posh = pos.contiguous().pin_memory()
+    tickets = []
+    for i in range(2):
+        tk = C.c_int32()
+        _lib.check(lib.sm_track_host_async(m.handle, 0, B, xs[i].data_ptr(), outs[i][0].data_ptr(),
+                                           outs[i][1].data_ptr(), posh.data_ptr(), outs[i][2].data_ptr(), st, C.byref(tk)))
+        tickets.append(tk.value)
+    for i in range(2):
+        _lib.check(lib.sm_track_host_wait(m.handle, tickets[i]))
+        for got, r, n in zip(outs[i], want[i], ("cls", "loc", "refine")):
+            assert_close(got, r, 1e-6, f"two-lane host path {n} step {i}")
+
+
 def test_search_383_response_41(calib_sd):
     g = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, "rpn_b1_s383.npz")).items()}
     z, x = synthetic_inputs(3, 1, search=383)
