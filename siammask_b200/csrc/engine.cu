@@ -75,17 +75,18 @@ struct Arena {
   }
 };
 
-// One execution lane: its own workspace, stream set and cached per-step tensors.  A batch of >= kLaneMinB streams
-// is split over two lanes that run concurrently (streams are independent): the persistent GEMM kernels of one lane
+// One execution lane: its own workspace, stream set and cached per-step tensors.  A batch of >= 2 * kLaneMinB streams
+// is split over two (SMB200_LANES: up to kMaxLanes) lanes that run concurrently (streams are independent): the persistent GEMM kernels of one lane
 // fill the SMs the other lane's kernels leave idle in their last wave and in the low-occupancy refine tail.
 struct Lane {
   Arena search, refine;
   std::map<std::string, Act> named;            // p0, p1, p2, search, corr_* of the lane's last track
-  cudaStream_t own = nullptr;                  // lane 1 only: its main stream (lane 0 runs on the caller's stream)
+  cudaStream_t own = nullptr;                  // the lane's main stream (lane 0 runs on the caller's stream in the device-pointer API)
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
   int cap_B = 0;                               // largest batch this lane's arenas were sized for
 };
-constexpr int kLaneMinB = 16;
+constexpr int kMaxLanes = 4;
+constexpr int kLaneMinB = 8;                   // a lane gets at least this many streams (below 2 x 8: one lane)
 
 }  // namespace
 
@@ -164,10 +165,11 @@ class Engine {
   bool weights_ready_ = false;
 
   Arena templ_arena_;
-  Lane lanes_[2];
+  Lane lanes_[kMaxLanes];
   Lane* cur_ = &lanes_[0];             // lane whose schedule is being enqueued
-  int n_lanes_ = 1;                    // 2 when max_batch >= kLaneMinB (SMB200_LANES=1 disables)
-  int split_n_ = 1, split_B0_ = 0;     // how the last track divided its batch
+  int n_lanes_ = 1;                    // SMB200_LANES (default 2), capped by max_batch / kLaneMinB
+  int split_n_ = 1;                    // how the last track divided its batch: lane l got streams
+  int split_off_[kMaxLanes + 1] = {0, 0, 0, 0, 0};   //   [split_off_[l], split_off_[l + 1])
   // per-slot template caches: [branch][slot][5][5][256] split planes, and zf for export
   __half* kcache_hi_ = nullptr;
   __half* kcache_lo_ = nullptr;
@@ -211,8 +213,9 @@ class Engine {
   struct GraphEntry {
     int seen = 0;
     cudaGraphExec_t exec = nullptr;
-    std::map<std::string, Act> named[2];
-    int split_n = 1, split_B0 = 0;
+    std::map<std::string, Act> named[kMaxLanes];
+    int split_n = 1;
+    int split_off[kMaxLanes + 1] = {0, 0, 0, 0, 0};
     int last_B = 0;
     bool have_mask_feats = false;
     int64_t launches = 0;
@@ -224,17 +227,50 @@ class Engine {
   void refine_impl(int B, const int32_t* pos, float* out, cudaStream_t st);
   void refine_lane(int B, const int32_t* pos, float* out, cudaStream_t st);
   bool defer_join_ = false;            // host-buffer path: lane 1 stays forked between its track and its refine
-  bool lane1_forked_ = false;
+  bool lane1_forked_ = false;          // lanes 1.. are forked from the caller's stream and not joined back yet
+  // host-buffer path with two lanes: both lanes run on their own streams and are never joined into the caller's
+  // stream — each only waits for its inputs, the D2H waits for both — so consecutive steps of the two lanes slide
+  // against each other.  The next stream-ordered entry point (template / track / refine / export) joins them.
+  bool lanes_dirty_ = false;
+  cudaEvent_t lane_done_[2][kMaxLanes] = {};   // [staging set][lane]
+  void join_lanes(cudaStream_t st) {
+    if (!lanes_dirty_) return;
+    for (int l = 0; l < n_lanes_; ++l) order_after(lanes_[l].own, st);
+    lanes_dirty_ = false;
+  }
+  static int lanes_for(int n_lanes, int B) { return std::max(1, std::min(n_lanes, B / kLaneMinB)); }
+  static int chunk(int B, int nl, int l) { return B / nl + (l < B % nl ? 1 : 0); }
+  void split_batch(int B) {
+    // per-launch profiling (bench.py roofline) times every layer as ONE launch over the whole batch: per-kernel
+    // durations are not defined while two lanes interleave, and half-batch launches timed back to back would charge
+    // each kernel the idle last wave that the other lane fills in the real schedule
+    split_n_ = profiling_ ? 1 : lanes_for(n_lanes_, B);
+    split_off_[0] = 0;
+    for (int l = 0; l < split_n_; ++l) {
+      split_off_[l + 1] = split_off_[l] + chunk(B, split_n_, l);
+      SMK_CHECK(chunk(B, split_n_, l) <= lanes_[l].cap_B, "lane workspace too small for this batch");
+    }
+  }
+  void fork_lanes(cudaStream_t st) {
+    if (split_n_ < 2 || !concurrent() || lane1_forked_) return;
+    for (int l = 1; l < split_n_; ++l) order_after(st, lanes_[l].own);
+    lane1_forked_ = true;
+  }
+  void join_forked(cudaStream_t st) {
+    if (!lane1_forked_) return;
+    for (int l = 1; l < n_lanes_; ++l) order_after(lanes_[l].own, st);
+    lane1_forked_ = false;
+  }
   template <typename F>
   void run_with_graph(const std::vector<uint64_t>& key, cudaStream_t st, F&& body) {
     if (!use_graphs_ || profiling_) { body(); return; }
     GraphEntry& ge = graphs_[key];
     if (ge.exec != nullptr) {
       SMK_CUDA(cudaGraphLaunch(ge.exec, st));
-      for (int l = 0; l < 2; ++l)
+      for (int l = 0; l < kMaxLanes; ++l)
         for (auto& kv : ge.named[l]) lanes_[l].named[kv.first] = kv.second;
       split_n_ = ge.split_n;
-      split_B0_ = ge.split_B0;
+      for (int l = 0; l <= kMaxLanes; ++l) split_off_[l] = ge.split_off[l];
       last_B_ = ge.last_B;
       have_mask_feats_ = ge.have_mask_feats;
       launches_ += ge.launches;
@@ -254,9 +290,9 @@ class Engine {
     SMK_CUDA(cudaStreamEndCapture(st, &graph));
     SMK_CUDA(cudaGraphInstantiate(&ge.exec, graph, 0));
     SMK_CUDA(cudaGraphDestroy(graph));
-    for (int l = 0; l < 2; ++l) ge.named[l] = lanes_[l].named;
+    for (int l = 0; l < kMaxLanes; ++l) ge.named[l] = lanes_[l].named;
     ge.split_n = split_n_;
-    ge.split_B0 = split_B0_;
+    for (int l = 0; l <= kMaxLanes; ++l) ge.split_off[l] = split_off_[l];
     ge.last_B = last_B_;
     ge.have_mask_feats = have_mask_feats_;
     ge.launches = launches_ - l0;
@@ -449,10 +485,16 @@ Engine::Engine(const sm_config& cfg) : cfg_(cfg), exact_(cfg.precision == SM_PRE
   // workspace sizes: dry-run the schedule with a measuring arena
   {
     const char* e = std::getenv("SMB200_LANES");
-    n_lanes_ = (cfg.max_batch >= kLaneMinB && !(e != nullptr && atoi(e) == 1)) ? 2 : 1;
+    const int want = e != nullptr ? std::max(1, std::min(kMaxLanes, atoi(e))) : 2;
+    n_lanes_ = lanes_for(want, cfg.max_batch);
   }
-  lanes_[0].cap_B = n_lanes_ == 2 ? std::max((cfg.max_batch + 1) / 2, std::min(cfg.max_batch, kLaneMinB - 1)) : cfg.max_batch;
-  lanes_[1].cap_B = n_lanes_ == 2 ? cfg.max_batch / 2 : 0;
+  // the largest chunk each lane can be handed over all batch sizes this engine accepts (lane 0: the whole batch,
+  // when profiling)
+  lanes_[0].cap_B = cfg.max_batch;
+  for (int B = 1; B <= cfg.max_batch; ++B) {
+    const int nl = lanes_for(n_lanes_, B);
+    for (int l = 0; l < nl; ++l) lanes_[l].cap_B = std::max(lanes_[l].cap_B, chunk(B, nl, l));
+  }
   templ_arena_.cap = measure_arena(cfg.max_batch, 127, false);
   SMK_CUDA(cudaMalloc(&templ_arena_.base, templ_arena_.cap));
   for (int l = 0; l < n_lanes_; ++l) {
@@ -465,7 +507,7 @@ Engine::Engine(const sm_config& cfg) : cfg_(cfg), exact_(cfg.precision == SM_PRE
       SMK_CUDA(cudaMalloc(&ln.refine.base, ln.refine.cap));
     }
     for (int i = 0; i < kAux; ++i) SMK_CUDA(cudaStreamCreateWithFlags(&ln.aux[i], cudaStreamNonBlocking));
-    if (l == 1) SMK_CUDA(cudaStreamCreateWithFlags(&ln.own, cudaStreamNonBlocking));
+    SMK_CUDA(cudaStreamCreateWithFlags(&ln.own, cudaStreamNonBlocking));
   }
   const size_t kc = (size_t)n_branches_ * cfg.num_slots * 25 * 256;
   SMK_CUDA(cudaMalloc(&kcache_hi_, kc * sizeof(__half)));
@@ -483,6 +525,7 @@ Engine::Engine(const sm_config& cfg) : cfg_(cfg), exact_(cfg.precision == SM_PRE
     SMK_CUDA(cudaEventCreateWithFlags(&h2d_done_[i], cudaEventDisableTiming));
     SMK_CUDA(cudaEventCreateWithFlags(&compute_done_[i], cudaEventDisableTiming));
     SMK_CUDA(cudaEventCreateWithFlags(&d2h_done_[i], cudaEventDisableTiming));
+    for (int l = 0; l < kMaxLanes; ++l) SMK_CUDA(cudaEventCreateWithFlags(&lane_done_[i][l], cudaEventDisableTiming));
   }
   SMK_CUDA(cudaStreamCreateWithFlags(&h2d_stream_, cudaStreamNonBlocking));
   SMK_CUDA(cudaStreamCreateWithFlags(&d2h_stream_, cudaStreamNonBlocking));
@@ -502,8 +545,9 @@ Engine::Engine(const sm_config& cfg) : cfg_(cfg), exact_(cfg.precision == SM_PRE
   sync_events_.resize(64);
   for (auto& e : sync_events_) SMK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
-  total_bytes_ = blob_bytes_ + templ_arena_.cap + lanes_[0].search.cap + lanes_[0].refine.cap + lanes_[1].search.cap +
-                 lanes_[1].refine.cap + 2 * kc * sizeof(__half) +
+  size_t lane_bytes = 0;
+  for (auto& ln : lanes_) lane_bytes += ln.search.cap + ln.refine.cap;
+  total_bytes_ = blob_bytes_ + templ_arena_.cap + lane_bytes + 2 * kc * sizeof(__half) +
                  2 * (B * 3 * S * S + B * 6 * A * R_ * R_ + B * 127 * 127) * sizeof(float);
 }
 
@@ -523,6 +567,7 @@ Engine::~Engine() {
     if (h2d_done_[i]) cudaEventDestroy(h2d_done_[i]);
     if (compute_done_[i]) cudaEventDestroy(compute_done_[i]);
     if (d2h_done_[i]) cudaEventDestroy(d2h_done_[i]);
+    for (int l = 0; l < kMaxLanes; ++l) if (lane_done_[i][l]) cudaEventDestroy(lane_done_[i][l]);
   }
   if (h2d_stream_) cudaStreamDestroy(h2d_stream_);
   if (d2h_stream_) cudaStreamDestroy(d2h_stream_);
@@ -840,6 +885,7 @@ static const char* kCorrName[3] = {"corr_cls", "corr_loc", "corr_mask"};
 void Engine::do_template(int slot0, int B, const float* z, cudaStream_t st) {
   SMK_CHECK(weights_ready_, "weights not loaded");
   SMK_CHECK(B >= 1 && B <= cfg_.max_batch && slot0 >= 0 && slot0 + B <= cfg_.num_slots, "template batch/slot range");
+  join_lanes(st);
   templ_arena_.reset();
   Act zf = backbone(z, B, 127, templ_arena_, false, st);
   SMK_CHECK(zf.H == 7 && zf.W == 7, "template feature must be 7x7");
@@ -859,6 +905,7 @@ void Engine::do_template(int slot0, int B, const float* z, cudaStream_t st) {
 
 void Engine::do_track(int slot0, int B, const float* x, float* cls, float* loc, float* mask, int flags,
                       cudaStream_t st) {
+  join_lanes(st);
   const std::vector<uint64_t> key = {1, (uint64_t)slot0, (uint64_t)B, (uint64_t)x, (uint64_t)cls, (uint64_t)loc,
                                      (uint64_t)mask, (uint64_t)flags, (uint64_t)st};
   run_with_graph(key, st, [&] { track_impl(slot0, B, x, cls, loc, mask, flags, st); });
@@ -874,23 +921,20 @@ void Engine::track_impl(int slot0, int B, const float* x, float* cls, float* loc
   SMK_CHECK(!(want_feats || want_mask_head) || cfg_.with_mask, "engine was built without the mask branch");
   SMK_CHECK(!want_mask_head || mask != nullptr, "mask output buffer required");
   // split the streams over the two lanes; lane 1 forks from / joins back into the caller's stream
-  const int nl = (n_lanes_ == 2 && B >= kLaneMinB) ? 2 : 1;
-  const int B0 = nl == 2 ? (B + 1) / 2 : B;
-  SMK_CHECK(B0 <= lanes_[0].cap_B && B - B0 <= lanes_[1].cap_B, "lane workspace too small for this batch");
-  split_n_ = nl;
-  split_B0_ = B0;
+  split_batch(B);
+  const int nl = split_n_;
   const size_t S = cfg_.search_size, A = cfg_.anchor_num, RR = (size_t)R_ * R_;
   // fork before anything of this call is enqueued on `st`, so the lanes really run side by side
-  if (nl == 2 && concurrent() && !lane1_forked_) { order_after(st, lanes_[1].own); lane1_forked_ = true; }
+  fork_lanes(st);
   for (int l = nl - 1; l >= 0; --l) {
     cur_ = &lanes_[l];
-    const int b0 = l == 0 ? 0 : B0, nbat = l == 0 ? B0 : B - B0;
-    cudaStream_t ls = (l == 0 || !concurrent()) ? st : lanes_[1].own;
+    const int b0 = split_off_[l], nbat = split_off_[l + 1] - split_off_[l];
+    cudaStream_t ls = (l == 0 || !concurrent()) ? st : lanes_[l].own;
     track_lane(slot0 + b0, nbat, x + b0 * 3 * S * S, cls + b0 * 2 * A * RR, loc + b0 * 4 * A * RR,
                mask != nullptr ? mask + (size_t)b0 * 63 * 63 * RR : nullptr, flags, ls);
   }
   cur_ = &lanes_[0];
-  if (lane1_forked_ && !defer_join_) { order_after(lanes_[1].own, st); lane1_forked_ = false; }
+  if (!defer_join_) join_forked(st);
   last_B_ = B;
   have_mask_feats_ = want_feats || want_mask_head;
 }
@@ -954,6 +998,7 @@ F32T Engine::small(const F32T& a, const F32T* b, int Ho, const ConvW& Lw, bool r
 // Refine.forward(test=True), custom.py:131-154, one (dy,dx) per stream
 void Engine::do_refine(int B, const int32_t* pos, float* out, cudaStream_t st) {
   SMK_CHECK(have_mask_feats_ && B == last_B_, "sm_refine must follow sm_track(..., SM_TRACK_MASK_FEATURES) with the same B");
+  join_lanes(st);
   const std::vector<uint64_t> key = {2, (uint64_t)B, (uint64_t)pos, (uint64_t)out, (uint64_t)st,
                                      (uint64_t)lanes_[0].named["p0"].hi};
   run_with_graph(key, st, [&] { refine_impl(B, pos, out, st); });
@@ -963,15 +1008,15 @@ void Engine::refine_impl(int B, const int32_t* pos, float* out, cudaStream_t st)
   SMK_CHECK(cfg_.with_mask, "engine was built without the mask branch");
   SMK_CHECK(have_mask_feats_ && B == last_B_, "sm_refine must follow sm_track(..., SM_TRACK_MASK_FEATURES) with the same B");
   // same split as the track that cached the features
-  if (split_n_ == 2 && concurrent() && !lane1_forked_) { order_after(st, lanes_[1].own); lane1_forked_ = true; }
+  fork_lanes(st);
   for (int l = split_n_ - 1; l >= 0; --l) {
     cur_ = &lanes_[l];
-    const int b0 = l == 0 ? 0 : split_B0_, nbat = l == 0 ? split_B0_ : B - split_B0_;
-    cudaStream_t ls = (l == 0 || !concurrent()) ? st : lanes_[1].own;
+    const int b0 = split_off_[l], nbat = split_off_[l + 1] - split_off_[l];
+    cudaStream_t ls = (l == 0 || !concurrent()) ? st : lanes_[l].own;
     refine_lane(nbat, pos + 2 * b0, out + (size_t)b0 * 127 * 127, ls);
   }
   cur_ = &lanes_[0];
-  if (lane1_forked_) { order_after(lanes_[1].own, st); lane1_forked_ = false; }
+  join_forked(st);
 }
 
 void Engine::refine_lane(int B, const int32_t* pos, float* out, cudaStream_t st) {
@@ -1053,6 +1098,30 @@ int Engine::track_host_async(int slot0, int B, const float* xh, float* clsh, flo
   if (refine)
     SMK_CUDA(cudaMemcpyAsync(stage_pos_[t], posh, (size_t)B * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, h2d_stream_));
   SMK_CUDA(cudaEventRecord(h2d_done_[t], h2d_stream_));
+  if (lanes_for(n_lanes_, B) >= 2 && !use_graphs_ && concurrent()) {
+    // decoupled lanes (see lanes_dirty_): order them after the caller's stream once (templates written there), then
+    // each lane only depends on its inputs
+    SMK_CHECK(weights_ready_, "weights not loaded");
+    SMK_CHECK(slot0 >= 0 && slot0 + B <= cfg_.num_slots, "track batch/slot range");
+    SMK_CHECK(!refine || cfg_.with_mask, "engine was built without the mask branch");
+    split_batch(B);
+    for (int l = split_n_ - 1; l >= 0; --l) {
+      cur_ = &lanes_[l];
+      cudaStream_t ls = cur_->own;
+      const int b0 = split_off_[l], nbat = split_off_[l + 1] - split_off_[l];
+      order_after(st, ls);
+      SMK_CUDA(cudaStreamWaitEvent(ls, h2d_done_[t], 0));
+      track_lane(slot0 + b0, nbat, stage_x_[t] + b0 * 3 * S * S, stage_cls_[t] + b0 * 2 * A * R_ * R_,
+                 stage_loc_[t] + b0 * 4 * A * R_ * R_, nullptr, refine ? SM_TRACK_MASK_FEATURES : 0, ls);
+      if (refine) refine_lane(nbat, stage_pos_[t] + 2 * b0, stage_mask_[t] + (size_t)b0 * 127 * 127, ls);
+      SMK_CUDA(cudaEventRecord(lane_done_[t][l], ls));
+      SMK_CUDA(cudaStreamWaitEvent(d2h_stream_, lane_done_[t][l], 0));
+    }
+    cur_ = &lanes_[0];
+    last_B_ = B;
+    have_mask_feats_ = refine;
+    lanes_dirty_ = true;
+  } else {
   SMK_CUDA(cudaStreamWaitEvent(st, h2d_done_[t], 0));
   // lane 1 stays forked between its track and its refine (nobody reads cls/loc on `st` in between)
   defer_join_ = refine && !use_graphs_;
@@ -1066,6 +1135,7 @@ int Engine::track_host_async(int slot0, int B, const float* xh, float* clsh, flo
   if (refine) do_refine(B, stage_pos_[t], stage_mask_[t], st);
   SMK_CUDA(cudaEventRecord(compute_done_[t], st));
   SMK_CUDA(cudaStreamWaitEvent(d2h_stream_, compute_done_[t], 0));
+  }
   SMK_CUDA(cudaMemcpyAsync(clsh, stage_cls_[t], ncls * sizeof(float), cudaMemcpyDeviceToHost, d2h_stream_));
   SMK_CUDA(cudaMemcpyAsync(loch, stage_loc_[t], nloc * sizeof(float), cudaMemcpyDeviceToHost, d2h_stream_));
   if (refine)
@@ -1088,6 +1158,7 @@ void Engine::track_host(int slot0, int B, const float* xh, float* clsh, float* l
 }
 
 void Engine::do_export(const char* what, float* out, int64_t* shape4, cudaStream_t st) {
+  join_lanes(st);
   if (std::string(what) == "zf") {
     SMK_CHECK(have_zf_, "no cached tensor named 'zf'");
     if (shape4 != nullptr) { shape4[0] = zf_.B; shape4[1] = zf_.C; shape4[2] = zf_.H; shape4[3] = zf_.W; }
