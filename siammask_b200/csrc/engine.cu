@@ -261,6 +261,16 @@ class Engine {
     for (int l = 1; l < n_lanes_; ++l) order_after(lanes_[l].own, st);
     lane1_forked_ = false;
   }
+  // if a schedule throws half way (arena exhausted, launch error), leave the lanes joined and lane 0 current
+  struct LaneGuard {
+    Engine* e; cudaStream_t st; bool armed = true;
+    ~LaneGuard() {
+      if (!armed) return;
+      e->cur_ = &e->lanes_[0];
+      e->defer_join_ = false;
+      try { e->join_forked(st); } catch (...) {}
+    }
+  };
   template <typename F>
   void run_with_graph(const std::vector<uint64_t>& key, cudaStream_t st, F&& body) {
     if (!use_graphs_ || profiling_) { body(); return; }
@@ -923,6 +933,7 @@ void Engine::track_impl(int slot0, int B, const float* x, float* cls, float* loc
   // split the streams over the two lanes; lane 1 forks from / joins back into the caller's stream
   split_batch(B);
   const int nl = split_n_;
+  LaneGuard guard{this, st};
   const size_t S = cfg_.search_size, A = cfg_.anchor_num, RR = (size_t)R_ * R_;
   // fork before anything of this call is enqueued on `st`, so the lanes really run side by side
   fork_lanes(st);
@@ -934,6 +945,7 @@ void Engine::track_impl(int slot0, int B, const float* x, float* cls, float* loc
                mask != nullptr ? mask + (size_t)b0 * 63 * 63 * RR : nullptr, flags, ls);
   }
   cur_ = &lanes_[0];
+  guard.armed = false;
   if (!defer_join_) join_forked(st);
   last_B_ = B;
   have_mask_feats_ = want_feats || want_mask_head;
@@ -1008,6 +1020,7 @@ void Engine::refine_impl(int B, const int32_t* pos, float* out, cudaStream_t st)
   SMK_CHECK(cfg_.with_mask, "engine was built without the mask branch");
   SMK_CHECK(have_mask_feats_ && B == last_B_, "sm_refine must follow sm_track(..., SM_TRACK_MASK_FEATURES) with the same B");
   // same split as the track that cached the features
+  LaneGuard guard{this, st};
   fork_lanes(st);
   for (int l = split_n_ - 1; l >= 0; --l) {
     cur_ = &lanes_[l];
@@ -1016,6 +1029,7 @@ void Engine::refine_impl(int B, const int32_t* pos, float* out, cudaStream_t st)
     refine_lane(nbat, pos + 2 * b0, out + (size_t)b0 * 127 * 127, ls);
   }
   cur_ = &lanes_[0];
+  guard.armed = false;
   join_forked(st);
 }
 
