@@ -89,11 +89,14 @@ print("variants ok")
 
 @pytest.mark.parametrize("env", [{"SMB200_CTA_PAIR": "0"}, {"SMB200_CTA_PAIR": "3"},
                                  {"SMB200_CTA_PAIR": "2", "SMB200_EXACT_N256": "0"},
-                                 {"SMB200_CTA_PAIR": "0", "SMB200_EXACT_N256": "3"}],
-                         ids=["single_cta", "pairs_everywhere", "pairs_128wide", "wide_single"])
+                                 {"SMB200_CTA_PAIR": "0", "SMB200_EXACT_N256": "3"},
+                                 {"SMB200_CTA_PAIR": "1", "SMB200_EXACT_N256": "3"}],
+                         ids=["single_cta", "pairs_everywhere", "pairs_128wide", "wide_single", "wide_pairs"])
 def test_conv_tile_variants(env):
-    """The launcher picks the tile (128x128 / 128x256 / CTA-pair 256x256, 256x128) per layer; the switches are read
-    once per process, so the non-default kernels are exercised in a child process."""
+    """The launcher picks the tile (128x128 / 128x256 / CTA-pair 256x256, 256x128) per layer and problem size (the
+    wide / pair tiles only when the 128x128 tiling fills the machine, i.e. not at these test sizes); the switches are
+    read once per process, so every kernel variant is forced in a child process ("wide_pairs" = what the long-K layers
+    run at bench.py's batch)."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
