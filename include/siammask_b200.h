@@ -113,7 +113,10 @@ int sm_track_host(sm_engine* e, int32_t slot0, int32_t B, const float* x_host, f
 /* Asynchronous form of sm_track_host: returns at once with a ticket (0/1); sm_track_host_wait(ticket) blocks
  * until that step's results are in the host buffers.  Two staging sets alternate, so submitting step k+1 before
  * waiting for step k overlaps its H2D (and step k's D2H) with compute.  Host buffers must stay valid (and pinned,
- * for real overlap) until the wait returns. */
+ * for real overlap) until the wait returns.  For B >= 16 the two halves of the batch run on two internal lanes
+ * (own streams) that are ordered only by the ticket: the results are defined after sm_track_host_wait, not by
+ * `stream` order; the next stream-ordered entry point (sm_template / sm_track / sm_refine / sm_export) joins the lanes
+ * into its stream first. */
 int sm_track_host_async(sm_engine* e, int32_t slot0, int32_t B, const float* x_host, float* cls_host, float* loc_host,
                         const int32_t* pos_host, float* mask_out_host, void* stream, int32_t* ticket);
 int sm_track_host_wait(sm_engine* e, int32_t ticket);

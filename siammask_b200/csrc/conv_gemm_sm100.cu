@@ -25,6 +25,13 @@
 //
 // Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one lane),
 // warps 2..9 = epilogue (two per TMEM lane quarter).  Persistent: grid = min(tiles, SMs), static round-robin over (m_tile, n_tile).
+//
+// * CG = 2 runs the same kernel as a CTA PAIR (cluster of two, tcgen05 cta_group::2) on a 256 x BLOCK_N tile: each CTA
+//   stages its own 128 A rows and half of the B rows (TMA loads of both CTAs signal the leader's full barrier), the
+//   leader's MMA thread issues M=256 instructions that write both CTAs' TMEM and multicasts its commits to the pair's
+//   empty / accumulator-full barriers, the epilogue warps of both CTAs release the accumulator on the leader's barrier.
+//   Per flop this moves a third less through each SM's shared-memory port, the resource that caps the single-CTA
+//   exact-mode tiles at ~65 % tensor duty (see launch_gemm_multi for the tile choice and the measurements).
 #include "common.cuh"
 #include "ptx.cuh"
 
