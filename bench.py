@@ -144,7 +144,8 @@ def workload_config(args, batch_per_gpu, world):
                         f"mask head) + on-device score/box selection + track_refine at the selected position, {batch_per_gpu} paired streams per GPU, templates cached per slot",
             "global_batch": batch_per_gpu * world, "batch_per_gpu": batch_per_gpu, "search": args.search,
             "parallelism": f"streams sharded over {world} GPU(s), one NCCL weight broadcast at init, "
-                           "no per-frame collective",
+                           "no per-frame collective; inside a GPU the batch runs as two concurrent lanes of "
+                           "batch_per_gpu/2 streams (batches >= 16)",
             "l2": "inputs rotate over 4 device buffers (4 x 50 MB) and every step streams > 5 GB of activations "
                   "(>> 126 MB L2)"}
 
