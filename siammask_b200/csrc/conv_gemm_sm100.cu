@@ -476,9 +476,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
             const int b = m / HoWo;
             const int hw = m - b * HoWo;
             float* dst = ep.out_f32 + (static_cast<size_t>(b) * p.Cout + n) * HoWo + hw;
+            // write-once output: stream past L2.  The channel bound is warp-uniform: full chunks take the branch-free
+            // path with a running pointer (a per-store bound check + 64-bit multiply cost ~17 instructions per store)
+            if (n + CH <= p.Cout) {
 #pragma unroll
-            for (int j = 0; j < CH; ++j)
-              if (n + j < p.Cout) __stcs(dst + static_cast<size_t>(j) * HoWo, v[j]);   // write-once output: stream past L2
+              for (int j = 0; j < CH; ++j) {
+                __stcs(dst, v[j]);
+                dst += HoWo;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) {
+                if (n + j < p.Cout) __stcs(dst, v[j]);
+                dst += HoWo;
+              }
+            }
           }
         }
       }
