@@ -164,7 +164,7 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// mbarrier wait with a watchdog: traps instead of hanging the GPU if the phase never completes (~2 s)
+// mbarrier wait with a watchdog: traps instead of hanging the GPU if the phase never completes (~20 s)
 __device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   long long t0 = 0;
@@ -180,7 +180,7 @@ __device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity
     if (ok) return;
     const long long t = clock64();
     if (t0 == 0) t0 = t;
-    else if (t - t0 > 4000000000ll) __trap();
+    else if (t - t0 > 40000000000ll) __trap();   // ~20 s of SM clocks: far beyond any legitimate wait, even time-sliced
   }
 }
 // TMA loads issued by either CTA of a pair; the transaction bytes are signalled on `bar_cluster_addr`
