@@ -98,12 +98,44 @@ int sm_warp_affine(const float* src, int32_t src_h, int32_t src_w, const double*
 /* Score / box post-processing + argmax of siamese_track — tools/test.py:205-254 — on the device, so that
  * sm_track -> sm_select -> sm_refine needs no host round trip.  All pointers are device pointers:
  * cls/loc as returned by sm_track; anchors f32 [A*R*R][4] = (cx,cy,w,h) in generate_anchor order (tools/test.py:113-129);
- * window f32 [A*R*R] (tiled hanning, :157-161); target_sz_in_crop f32 [B][2] = target_sz * scale_x (:226).
- * Outputs: best_idx int32 [B] (np.argmax of pscore, :237), pos int32 [B][2] = (delta_y, delta_x) (:253-254),
- * records f32 [B][8] = decoded box cx,cy,w,h of the winner in crop units (:209-212), score, penalty, pscore, 0. */
+ * window f32 [A*R*R] (tiled hanning, :157-161); target_sz_in_crop f64 [B][2] = target_sz * scale_x (:226; float64 as
+ * in the reference, whose penalty terms are evaluated in float64).
+ * Outputs: best_idx int32 [B] (np.argmax of pscore, :237 — incl. its NaN rule: the first NaN wins), pos int32 [B][2] =
+ * (delta_y, delta_x) (:253-254), records f32 [B][8] = decoded box cx,cy,w,h of the winner in crop units (:209-212),
+ * score, penalty, pscore, best index (exact: < 2^24). */
 int sm_select(sm_engine* e, int32_t B, const float* cls, const float* loc, const float* anchors, const float* window,
-              const float* target_sz_in_crop, double penalty_k, double window_influence, int32_t* best_idx, int32_t* pos,
+              const double* target_sz_in_crop, double penalty_k, double window_influence, int32_t* best_idx, int32_t* pos,
               float* records, void* stream);
+
+/* One whole frame of siamese_track (tools/test.py:201-261) on the device, all pointers device pointers:
+ * sm_track(flags) -> sm_select -> sm_refine at the position sm_select chose (refine_out != NULL needs
+ * SM_TRACK_MASK_FEATURES) -> optionally mask_col f32 [B][3969] = mask[b, :, dy, dx] (:259-260; needs
+ * SM_TRACK_MASK_HEAD and `mask`).  Unlike the three separate calls, the engine's two lanes run their halves of the
+ * batch start to end without meeting in between.  refine_out / mask / mask_col may be NULL. */
+int sm_step(sm_engine* e, int32_t slot0, int32_t B, const float* x_nchw, const double* target_sz_in_crop,
+            const float* anchors, const float* window, double penalty_k, double window_influence, int32_t flags,
+            float* cls, float* loc, float* mask, int32_t* best_idx, int32_t* pos, float* records, float* refine_out,
+            float* mask_col, void* stream);
+
+/* The same frame through HOST buffers: H2D of x and target_sz_in_crop, sm_step on staging buffers, D2H of the
+ * records (always) and of whichever of refine / mask_col / cls / loc are non-NULL.  anchors / window stay device
+ * pointers (per-tracker constants, tools/test.py:142-161).  Asynchronous with the ticket protocol of
+ * sm_track_host_async (wait with sm_track_host_wait); with SM_TRACK_MASK_HEAD the raw 3969-channel head output stays on
+ * the device (the reference reads one column of it, :259-260). */
+typedef struct sm_step_io {
+  const float* x_host;        /* f32 [B,3,S,S] */
+  const double* tsz_host;     /* f64 [B,2] target_sz * scale_x */
+  const float* anchors_dev;   /* f32 [A*R*R,4] device */
+  const float* window_dev;    /* f32 [A*R*R] device */
+  double penalty_k, window_influence;
+  int32_t flags;              /* SM_TRACK_* */
+  float* records_host;        /* f32 [B,8], required */
+  float* refine_host;         /* f32 [B,127*127] or NULL */
+  float* mask_col_host;       /* f32 [B,3969] or NULL */
+  float* cls_host;            /* f32 [B,2A,R,R] or NULL */
+  float* loc_host;            /* f32 [B,4A,R,R] or NULL */
+} sm_step_io;
+int sm_step_host_async(sm_engine* e, int32_t slot0, int32_t B, const sm_step_io* io, void* stream, int32_t* ticket);
 
 /* Whole step through HOST buffers (pinned recommended): H2D of x, track(+mask features), optional refine,
  * D2H of cls / loc / refine logits, then stream synchronise.  mask_out_host may be NULL (no refine). */

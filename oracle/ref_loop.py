@@ -1,4 +1,12 @@
-"""Host side of the tracker loop around the hot path (SURVEY §8f "next" rows): a restatement of
+"""TEST INFRASTRUCTURE ONLY (checker).  Nothing under `siammask_b200/` imports this module.
+
+Host restatement of the reference tracker loop, kept next to the other oracles because its integer / float64
+arithmetic has to match the reference statement for statement: it pins the product's batched device tracker
+(`siammask_b200/tracker.py`, kernels `tracker_prepare_kernel` / `tracker_update_kernel`) and the device crop / select /
+paste-back operators to the golden trajectory that the reference's OWN `siamese_init` / `siamese_track` produced
+(`oracle/make_golden.py::tracker_loop_golden`).
+
+A restatement of
 `generate_anchor`, `siamese_init` and `siamese_track` (tools/test.py:113-315) that drives a `net` exposing the
 reference's model API.  With a siammask_b200 engine the score/box post-processing + argmax between `track_mask`
 and `track_refine` (tools/test.py:205-254) runs on the device (`Custom.select`, C ABI `sm_select`), so the only
@@ -104,7 +112,7 @@ def get_subwindow_tracking(im, pos, model_sz, original_sz, avg_chans):
     """tools/test.py:67-110: crop a square window around pos (padding with the frame's mean colour), resize to
     model_sz with cv2.resize, return a float CHW tensor of raw 0..255 pixels."""
     if isinstance(im, torch.Tensor):         # frame already on the GPU: crop + cv2-exact resize on the device
-        from .ops import crop_resize
+        from siammask_b200.ops import crop_resize
         return crop_resize(im, [subwindow_box(pos, original_sz, avg_chans)], int(model_sz))[0]
     sz = original_sz
     im_sz = im.shape
@@ -225,10 +233,10 @@ def siamese_track(state, im, mask_enable=False, refine_enable=False, device="cud
     pos_dev = None
     if hasattr(net, "select"):
         best_t, pos_dev, rec = net.select(score, delta, state["anchor_dev"], state["window_dev"],
-                                          torch.tensor(tsz_crop[None], dtype=torch.float32), p.penalty_k,
+                                          torch.tensor(tsz_crop[None], dtype=torch.float64), p.penalty_k,
                                           p.window_influence)
-        rec = rec[0].cpu().numpy()        # the one host round trip of the frame (8 floats)
-        best_id, box, best_score, best_pen = int(best_t[0]), rec[:4].astype(np.float64), float(rec[4]), float(rec[5])
+        rec = rec[0].cpu().numpy()        # the one host round trip of the frame (8 floats; rec[7] = best index)
+        best_id, box, best_score, best_pen = int(rec[7]), rec[:4].astype(np.float64), float(rec[4]), float(rec[5])
     else:
         best_id, box, best_score, best_pen, _ = select_numpy(score, delta, p.anchor, window, tsz_crop, p.penalty_k,
                                                              p.window_influence)
@@ -257,7 +265,7 @@ def siamese_track(state, im, mask_enable=False, refine_enable=False, device="cud
             b = (out_sz[1] - 1) / bbox[3]
             mapping = np.array([[a, 0, -a * bbox[0]], [0, b, -b * bbox[1]]]).astype(float)
             if on_dev:
-                from .ops import warp_affine
+                from siammask_b200.ops import warp_affine
                 return warp_affine(image, mapping, (out_sz[0], out_sz[1]), padding)
             return cv2.warpAffine(image, mapping, (out_sz[0], out_sz[1]), flags=cv2.INTER_LINEAR,
                                   borderMode=cv2.BORDER_CONSTANT, borderValue=padding)

@@ -25,6 +25,13 @@ class SmTensorDesc(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int32), ("shape", C.c_int64 * 4)]
 
 
+class SmStepIO(C.Structure):
+    _fields_ = [("x_host", C.c_void_p), ("tsz_host", C.c_void_p), ("anchors_dev", C.c_void_p),
+                ("window_dev", C.c_void_p), ("penalty_k", C.c_double), ("window_influence", C.c_double),
+                ("flags", C.c_int32), ("records_host", C.c_void_p), ("refine_host", C.c_void_p),
+                ("mask_col_host", C.c_void_p), ("cls_host", C.c_void_p), ("loc_host", C.c_void_p)]
+
+
 # name -> (restype, argtypes); mirrors include/siammask_b200.h one to one
 SIGNATURES = {
     "sm_engine_create": (C.c_int, [C.POINTER(SmConfig), C.POINTER(C.c_void_p)]),
@@ -46,6 +53,10 @@ SIGNATURES = {
     "sm_warp_affine": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                  C.c_float, C.c_int32, C.c_void_p]),
     "sm_select": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 5 + [C.c_double, C.c_double] + [C.c_void_p] * 4),
+    "sm_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 4 + [C.c_double, C.c_double, C.c_int32] +
+                [C.c_void_p] * 9),
+    "sm_step_host_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(SmStepIO), C.c_void_p,
+                                     C.POINTER(C.c_int32)]),
     "sm_xcorr_depthwise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     "sm_conv2d": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 13 + [C.c_void_p]),
     "sm_export": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
@@ -66,16 +77,24 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    from . import build as _build
     if not os.path.exists(LIB_PATH):
         # a fresh checkout has sources only: compile the extension in-tree (nvcc, sm_100a) — there is no other
         # implementation to fall back to, so a failed build is a hard error
         try:
-            from . import build as _build
             _build.build(force=True)
         except Exception as exc:
             raise ImportError(
                 f"{LIB_PATH} is missing and could not be built ({exc}); build it with "
                 "`python -m siammask_b200.build`. siammask_b200 has no fallback implementation.") from exc
+    elif _build.is_stale():
+        # sources newer than the binary: never run edited kernels against an old .so silently
+        try:
+            _build.build(force=True)
+        except Exception as exc:
+            import warnings
+            warnings.warn(f"{LIB_PATH} is older than its sources and could not be rebuilt ({exc}); "
+                          "running the stale binary", RuntimeWarning)
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported

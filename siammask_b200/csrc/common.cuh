@@ -128,8 +128,10 @@ void launch_xcorr_nhwc(const Act& x, const __half* k_hi, const __half* k_lo, int
 void launch_xcorr_nchw_f32(const float* x, const float* k, float* out, int planes, int H, int W, int kh, int kw,
                            cudaStream_t st);
 void launch_crop_center(const Act& in, int crop, Act out, cudaStream_t st);
-void launch_refine_crop(const Act& in, const int32_t* pos, int scale, int padv, int size, Act out, cudaStream_t st);
+void launch_refine_crop(const Act& in, const int32_t* pos, int pos_max, int scale, int padv, int size, Act out,
+                        cudaStream_t st);
 void launch_gather_corr(const Act& corr, const int32_t* pos, float* out, cudaStream_t st);
+void launch_gather_mask_col(const float* mask, const int32_t* pos, int B, int C, int R, float* out, cudaStream_t st);
 void launch_deconv(const float* p3, const float* w, const float* bias, float* out, int B, int Cin, int N,
                    int cout, cudaStream_t st);
 void launch_split_to_f32(const Act& in, float* out, cudaStream_t st);
@@ -138,7 +140,7 @@ void launch_warp_affine(const float* src, int sh, int sw, const double* maps, fl
                         int B, cudaStream_t st);
 void launch_crop_resize(const uint8_t* frames, size_t frame_stride, int H, int W, const int32_t* box, int B, int model,
                         float* out, cudaStream_t st);
-void launch_select(const float* cls, const float* loc, const float* anchors, const float* window, const float* tsz,
+void launch_select(const float* cls, const float* loc, const float* anchors, const float* window, const double* tsz,
                    int B, int A, int R, double penalty_k, double window_influence, int32_t* best_idx, int32_t* pos,
                    float* rec, cudaStream_t st);
 // small-channel fp32 NHWC 3x3 pad-1 conv: in = up(a (+ b)); ymap/xmap: device nearest-upsample source indices

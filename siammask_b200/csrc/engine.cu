@@ -93,7 +93,7 @@ constexpr int kLaneMinB = 8;                   // a lane gets at least this many
 class Engine {
  public:
   explicit Engine(const sm_config& cfg);
-  ~Engine();
+  ~Engine() { release(); }
 
   void load_weights(const sm_tensor_desc* t, int n);
   void adopt_weights() { weights_ready_ = true; }
@@ -108,6 +108,21 @@ class Engine {
   int track_host_async(int slot0, int B, const float* xh, float* clsh, float* loch, const int32_t* posh, float* maskh,
                        cudaStream_t st);
   void host_wait(int ticket);
+  // whole frame: track(+mask) -> on-device score/box selection -> refine at the selected position
+  struct StepIO {
+    const float* x = nullptr;            // device or (host path) staged input
+    const double* tsz = nullptr;         // [B][2] target_sz * scale_x
+    const float* anchors = nullptr;      // device [A*R*R][4]
+    const float* window = nullptr;       // device [A*R*R]
+    double penalty_k = 0, window_influence = 0;
+    int flags = 0;
+    float* cls = nullptr; float* loc = nullptr; float* mask = nullptr;   // device outputs (mask: raw 3969-ch head)
+    int32_t* best = nullptr; int32_t* pos = nullptr; float* rec = nullptr;
+    float* refine = nullptr;             // [B][127*127] or null
+    float* mask_col = nullptr;           // [B][3969] = mask[b, :, dy, dx] or null
+  };
+  void do_step(int slot0, int B, const StepIO& io, cudaStream_t st);
+  int step_host_async(int slot0, int B, const sm_step_io& io, cudaStream_t st);
   void do_export(const char* what, float* out, int64_t* shape4, cudaStream_t st);
 
   void set_profiling(bool on) { profiling_ = on; }
@@ -118,6 +133,7 @@ class Engine {
 
  private:
   // ---- construction
+  void construct(const sm_config& cfg);
   ConvW& add_layer(const std::string& conv_key, const std::string& bn_key, ConvGeom g);
   void build_layer_table();
   void assign_blob_layout();
@@ -181,6 +197,13 @@ class Engine {
   float* stage_loc_[2] = {nullptr, nullptr};
   float* stage_mask_[2] = {nullptr, nullptr};
   int32_t* stage_pos_[2] = {nullptr, nullptr};
+  double* stage_tsz_[2] = {nullptr, nullptr};
+  float* stage_rec_[2] = {nullptr, nullptr};
+  int32_t* stage_best_[2] = {nullptr, nullptr};
+  float* stage_maskcol_[2] = {nullptr, nullptr};
+  float* mask_raw_ = nullptr;          // [max_batch][3969][R][R] raw mask-head output of the host-buffer step (lazy)
+  void step_lane(int slot0, int B, const StepIO& io, cudaStream_t st);
+  void release();
   cudaStream_t h2d_stream_ = nullptr, d2h_stream_ = nullptr;
   cudaEvent_t h2d_done_[2] = {nullptr, nullptr}, compute_done_[2] = {nullptr, nullptr}, d2h_done_[2] = {nullptr, nullptr};
   bool set_busy_[2] = {false, false};
@@ -457,6 +480,15 @@ void Engine::assign_blob_layout() {
 }
 
 Engine::Engine(const sm_config& cfg) : cfg_(cfg), exact_(cfg.precision == SM_PRECISION_EXACT) {
+  try {
+    construct(cfg);
+  } catch (...) {
+    release();           // a half-built engine must not leak its device allocations, streams and events
+    throw;
+  }
+}
+
+void Engine::construct(const sm_config& cfg) {
   SMK_CHECK(cfg.search_size >= 127 && (cfg.search_size - 127) % 8 == 0, "search_size must be 127 + 8k");
   SMK_CHECK(cfg.max_batch >= 1 && cfg.num_slots >= cfg.max_batch, "need num_slots >= max_batch >= 1");
   SMK_CHECK(cfg.anchor_num >= 1, "anchor_num");
@@ -532,6 +564,10 @@ Engine::Engine(const sm_config& cfg) : cfg_(cfg), exact_(cfg.precision == SM_PRE
     SMK_CUDA(cudaMalloc(&stage_loc_[i], B * 4 * A * R_ * R_ * sizeof(float)));
     SMK_CUDA(cudaMalloc(&stage_mask_[i], B * 127 * 127 * sizeof(float)));
     SMK_CUDA(cudaMalloc(&stage_pos_[i], B * 2 * sizeof(int32_t)));
+    SMK_CUDA(cudaMalloc(&stage_tsz_[i], B * 2 * sizeof(double)));
+    SMK_CUDA(cudaMalloc(&stage_rec_[i], B * 8 * sizeof(float)));
+    SMK_CUDA(cudaMalloc(&stage_best_[i], B * sizeof(int32_t)));
+    if (cfg_.with_mask) SMK_CUDA(cudaMalloc(&stage_maskcol_[i], B * 3969 * sizeof(float)));
     SMK_CUDA(cudaEventCreateWithFlags(&h2d_done_[i], cudaEventDisableTiming));
     SMK_CUDA(cudaEventCreateWithFlags(&compute_done_[i], cudaEventDisableTiming));
     SMK_CUDA(cudaEventCreateWithFlags(&d2h_done_[i], cudaEventDisableTiming));
@@ -561,7 +597,7 @@ Engine::Engine(const sm_config& cfg) : cfg_(cfg), exact_(cfg.precision == SM_PRE
                  2 * (B * 3 * S * S + B * 6 * A * R_ * R_ + B * 127 * 127) * sizeof(float);
 }
 
-Engine::~Engine() {
+void Engine::release() {
   cudaFree(blob_);
   cudaFree(templ_arena_.base);
   for (auto& ln : lanes_) {
@@ -574,6 +610,7 @@ Engine::~Engine() {
   cudaFree(kcache_lo_);
   for (int i = 0; i < 2; ++i) {
     cudaFree(stage_x_[i]); cudaFree(stage_cls_[i]); cudaFree(stage_loc_[i]); cudaFree(stage_mask_[i]); cudaFree(stage_pos_[i]);
+    cudaFree(stage_tsz_[i]); cudaFree(stage_rec_[i]); cudaFree(stage_best_[i]); cudaFree(stage_maskcol_[i]);
     if (h2d_done_[i]) cudaEventDestroy(h2d_done_[i]);
     if (compute_done_[i]) cudaEventDestroy(compute_done_[i]);
     if (d2h_done_[i]) cudaEventDestroy(d2h_done_[i]);
@@ -582,6 +619,7 @@ Engine::~Engine() {
   if (h2d_stream_) cudaStreamDestroy(h2d_stream_);
   if (d2h_stream_) cudaStreamDestroy(d2h_stream_);
   cudaFree(maps_dev_);
+  cudaFree(mask_raw_);
   for (auto e : sync_events_) cudaEventDestroy(e);
   for (auto e : event_pool_) cudaEventDestroy(e);
   for (auto& kv : graphs_) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -1053,7 +1091,7 @@ void Engine::refine_lane(int B, const int32_t* pos, float* out, cudaStream_t st)
   {
     Scope sc(this, "crop_p2", "refine_misc", 0, 8.0 * c2.numel(), s2);
     last_end_[c2.hi] = +1;
-    launch_refine_crop(p2, pos, 1, 4, 15, c2, s2); ++launches_;
+    launch_refine_crop(p2, pos, R_ - 1, 1, 4, 15, c2, s2); ++launches_;
   }
   Act v2a = conv(c2, L(R + "v2.0"), true, nullptr, ar, s2);
   F32T v2b = conv_f32(v2a, L(R + "v2.2"), true, ar, s2);
@@ -1062,7 +1100,7 @@ void Engine::refine_lane(int B, const int32_t* pos, float* out, cudaStream_t st)
   {
     Scope sc(this, "crop_p1", "refine_misc", 0, 8.0 * c1.numel(), s1);
     last_end_[c1.hi] = +1;
-    launch_refine_crop(p1, pos, 2, 8, 31, c1, s1); ++launches_;
+    launch_refine_crop(p1, pos, R_ - 1, 2, 8, 31, c1, s1); ++launches_;
   }
   Act v1a = conv(c1, L(R + "v1.0"), true, nullptr, ar, s1);
   F32T v1b = conv_f32(v1a, L(R + "v1.2"), true, ar, s1);
@@ -1071,7 +1109,7 @@ void Engine::refine_lane(int B, const int32_t* pos, float* out, cudaStream_t st)
   {
     Scope sc(this, "crop_p0", "refine_misc", 0, 8.0 * c0.numel(), s0);
     last_end_[c0.hi] = +1;
-    launch_refine_crop(p0, pos, 4, 16, 61, c0, s0); ++launches_;
+    launch_refine_crop(p0, pos, R_ - 1, 4, 16, 61, c0, s0); ++launches_;
   }
   F32T v0a = conv_f32(c0, L(R + "v0.0"), true, ar, s0);
   F32T v0b = small(v0a, nullptr, 61, L(R + "v0.2"), true, nullptr, ar, s0);
@@ -1169,6 +1207,139 @@ void Engine::host_wait(int ticket) {
 void Engine::track_host(int slot0, int B, const float* xh, float* clsh, float* loch, const int32_t* posh, float* maskh,
                         cudaStream_t st) {
   host_wait(track_host_async(slot0, B, xh, clsh, loch, posh, maskh, st));
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Whole frame of siamese_track (tools/test.py:201-261) without leaving the device: track(_mask) -> score/box
+// post-processing + argmax (:205-254) -> track_refine at the position that argmax selected (:253-257).  Each lane runs
+// its share of the streams start to end on its own stream; the lanes only meet at the end of the call.
+namespace {
+Engine::StepIO slice_io(const Engine::StepIO& io, int b0, size_t S, size_t A, size_t RR) {
+  Engine::StepIO o = io;
+  o.x = io.x + (size_t)b0 * 3 * S * S;
+  o.tsz = io.tsz + 2 * (size_t)b0;
+  o.cls = io.cls + (size_t)b0 * 2 * A * RR;
+  o.loc = io.loc + (size_t)b0 * 4 * A * RR;
+  if (io.mask) o.mask = io.mask + (size_t)b0 * 3969 * RR;
+  o.best = io.best + b0;
+  o.pos = io.pos + 2 * (size_t)b0;
+  o.rec = io.rec + 8 * (size_t)b0;
+  if (io.refine) o.refine = io.refine + (size_t)b0 * 127 * 127;
+  if (io.mask_col) o.mask_col = io.mask_col + (size_t)b0 * 3969;
+  return o;
+}
+}  // namespace
+
+void Engine::step_lane(int slot0, int B, const StepIO& io, cudaStream_t st) {
+  track_lane(slot0, B, io.x, io.cls, io.loc, io.mask, io.flags, st);
+  {
+    Scope sc(this, "select", "select", 0, 4.0 * B * 6.0 * cfg_.anchor_num * R_ * R_, st);
+    launch_select(io.cls, io.loc, io.anchors, io.window, io.tsz, B, cfg_.anchor_num, R_, io.penalty_k,
+                  io.window_influence, io.best, io.pos, io.rec, st);
+    ++launches_;
+  }
+  if (io.refine != nullptr) refine_lane(B, io.pos, io.refine, st);
+  if (io.mask_col != nullptr) {
+    launch_gather_mask_col(io.mask, io.pos, B, 3969, R_, io.mask_col, st);
+    ++launches_;
+  }
+}
+
+void Engine::do_step(int slot0, int B, const StepIO& io, cudaStream_t st) {
+  SMK_CHECK(weights_ready_, "weights not loaded");
+  SMK_CHECK(B >= 1 && B <= cfg_.max_batch && slot0 >= 0 && slot0 + B <= cfg_.num_slots, "step batch/slot range");
+  SMK_CHECK(io.x && io.tsz && io.anchors && io.window && io.cls && io.loc && io.best && io.pos && io.rec, "null argument");
+  const bool want_feats = (io.flags & SM_TRACK_MASK_FEATURES) != 0, want_head = (io.flags & SM_TRACK_MASK_HEAD) != 0;
+  SMK_CHECK(!(want_feats || want_head || io.refine) || cfg_.with_mask, "engine was built without the mask branch");
+  SMK_CHECK(io.refine == nullptr || want_feats, "refine output needs SM_TRACK_MASK_FEATURES");
+  SMK_CHECK(!want_head || io.mask != nullptr, "mask output buffer required");
+  SMK_CHECK(io.mask_col == nullptr || want_head, "mask column needs SM_TRACK_MASK_HEAD");
+  join_lanes(st);
+  const std::vector<uint64_t> key = {3, (uint64_t)slot0, (uint64_t)B, (uint64_t)io.x, (uint64_t)io.tsz, (uint64_t)io.cls,
+                                     (uint64_t)io.loc, (uint64_t)io.mask, (uint64_t)io.flags, (uint64_t)io.pos,
+                                     (uint64_t)io.rec, (uint64_t)io.refine, (uint64_t)io.mask_col, (uint64_t)st,
+                                     (uint64_t)io.anchors, (uint64_t)io.window};
+  run_with_graph(key, st, [&] {
+    split_batch(B);
+    LaneGuard guard{this, st};
+    const size_t S = cfg_.search_size, A = cfg_.anchor_num, RR = (size_t)R_ * R_;
+    fork_lanes(st);
+    for (int l = split_n_ - 1; l >= 0; --l) {
+      cur_ = &lanes_[l];
+      const int b0 = split_off_[l], nbat = split_off_[l + 1] - split_off_[l];
+      cudaStream_t ls = (l == 0 || !concurrent()) ? st : lanes_[l].own;
+      step_lane(slot0 + b0, nbat, slice_io(io, b0, S, A, RR), ls);
+    }
+    cur_ = &lanes_[0];
+    guard.armed = false;
+    join_forked(st);
+    last_B_ = B;
+    have_mask_feats_ = want_feats || want_head;
+  });
+}
+
+// Host-buffer form of do_step (pinned buffers recommended): H2D of the frames and of target_sz*scale_x, the whole
+// frame on the device, D2H of the per-stream records (+ refine logits / mask column / cls / loc when asked for).
+// Same ticket / staging-set protocol as track_host_async.
+int Engine::step_host_async(int slot0, int B, const sm_step_io& h, cudaStream_t st) {
+  const size_t S = cfg_.search_size, A = cfg_.anchor_num, RR = (size_t)R_ * R_;
+  SMK_CHECK(B >= 1 && B <= cfg_.max_batch, "batch");
+  SMK_CHECK(weights_ready_, "weights not loaded");
+  SMK_CHECK(slot0 >= 0 && slot0 + B <= cfg_.num_slots, "step batch/slot range");
+  SMK_CHECK(h.x_host && h.tsz_host && h.anchors_dev && h.window_dev && h.records_host, "null argument");
+  const bool want_feats = (h.flags & SM_TRACK_MASK_FEATURES) != 0, want_head = (h.flags & SM_TRACK_MASK_HEAD) != 0;
+  SMK_CHECK(!(want_feats || want_head || h.refine_host) || cfg_.with_mask, "engine was built without the mask branch");
+  SMK_CHECK(h.refine_host == nullptr || want_feats, "refine output needs SM_TRACK_MASK_FEATURES");
+  SMK_CHECK(h.mask_col_host == nullptr || want_head, "mask column needs SM_TRACK_MASK_HEAD");
+  if (want_head && mask_raw_ == nullptr)
+    SMK_CUDA(cudaMalloc(&mask_raw_, (size_t)cfg_.max_batch * 3969 * RR * sizeof(float)));
+  const int t = (int)(host_calls_++ & 1);
+  if (set_busy_[t]) host_wait(t);
+  SMK_CUDA(cudaMemcpyAsync(stage_x_[t], h.x_host, (size_t)B * 3 * S * S * sizeof(float), cudaMemcpyHostToDevice, h2d_stream_));
+  SMK_CUDA(cudaMemcpyAsync(stage_tsz_[t], h.tsz_host, (size_t)B * 2 * sizeof(double), cudaMemcpyHostToDevice, h2d_stream_));
+  SMK_CUDA(cudaEventRecord(h2d_done_[t], h2d_stream_));
+  StepIO io;
+  io.x = stage_x_[t]; io.tsz = stage_tsz_[t]; io.anchors = h.anchors_dev; io.window = h.window_dev;
+  io.penalty_k = h.penalty_k; io.window_influence = h.window_influence; io.flags = h.flags;
+  io.cls = stage_cls_[t]; io.loc = stage_loc_[t]; io.mask = want_head ? mask_raw_ : nullptr;
+  io.best = stage_best_[t]; io.pos = stage_pos_[t]; io.rec = stage_rec_[t];
+  io.refine = h.refine_host != nullptr ? stage_mask_[t] : nullptr;
+  io.mask_col = h.mask_col_host != nullptr ? stage_maskcol_[t] : nullptr;
+  if (lanes_for(n_lanes_, B) >= 2 && !use_graphs_ && concurrent()) {
+    split_batch(B);
+    for (int l = split_n_ - 1; l >= 0; --l) {
+      cur_ = &lanes_[l];
+      cudaStream_t ls = cur_->own;
+      const int b0 = split_off_[l], nbat = split_off_[l + 1] - split_off_[l];
+      order_after(st, ls);
+      SMK_CUDA(cudaStreamWaitEvent(ls, h2d_done_[t], 0));
+      step_lane(slot0 + b0, nbat, slice_io(io, b0, S, A, RR), ls);
+      SMK_CUDA(cudaEventRecord(lane_done_[t][l], ls));
+      SMK_CUDA(cudaStreamWaitEvent(d2h_stream_, lane_done_[t][l], 0));
+    }
+    cur_ = &lanes_[0];
+    last_B_ = B;
+    have_mask_feats_ = want_feats || want_head;
+    lanes_dirty_ = true;
+  } else {
+    SMK_CUDA(cudaStreamWaitEvent(st, h2d_done_[t], 0));
+    do_step(slot0, B, io, st);
+    SMK_CUDA(cudaEventRecord(compute_done_[t], st));
+    SMK_CUDA(cudaStreamWaitEvent(d2h_stream_, compute_done_[t], 0));
+  }
+  SMK_CUDA(cudaMemcpyAsync(h.records_host, stage_rec_[t], (size_t)B * 8 * sizeof(float), cudaMemcpyDeviceToHost, d2h_stream_));
+  if (h.refine_host)
+    SMK_CUDA(cudaMemcpyAsync(h.refine_host, stage_mask_[t], (size_t)B * 127 * 127 * sizeof(float), cudaMemcpyDeviceToHost, d2h_stream_));
+  if (h.mask_col_host)
+    SMK_CUDA(cudaMemcpyAsync(h.mask_col_host, stage_maskcol_[t], (size_t)B * 3969 * sizeof(float), cudaMemcpyDeviceToHost, d2h_stream_));
+  if (h.cls_host)
+    SMK_CUDA(cudaMemcpyAsync(h.cls_host, stage_cls_[t], (size_t)B * 2 * A * RR * sizeof(float), cudaMemcpyDeviceToHost, d2h_stream_));
+  if (h.loc_host)
+    SMK_CUDA(cudaMemcpyAsync(h.loc_host, stage_loc_[t], (size_t)B * 4 * A * RR * sizeof(float), cudaMemcpyDeviceToHost, d2h_stream_));
+  SMK_CUDA(cudaEventRecord(d2h_done_[t], d2h_stream_));
+  set_busy_[t] = true;
+  return t;
 }
 
 void Engine::do_export(const char* what, float* out, int64_t* shape4, cudaStream_t st) {
@@ -1397,6 +1568,28 @@ int sm_track_host_wait(sm_engine* e, int32_t ticket) {
   SM_API_END
 }
 
+int sm_step(sm_engine* e, int32_t slot0, int32_t B, const float* x, const double* target_sz_in_crop, const float* anchors,
+            const float* window, double penalty_k, double window_influence, int32_t flags, float* cls, float* loc,
+            float* mask, int32_t* best_idx, int32_t* pos, float* records, float* refine_out, float* mask_col,
+            void* stream) {
+  SM_API_BEGIN
+  SMK_CHECK(e, "null argument");
+  smk::Engine::StepIO io;
+  io.x = x; io.tsz = target_sz_in_crop; io.anchors = anchors; io.window = window;
+  io.penalty_k = penalty_k; io.window_influence = window_influence; io.flags = flags;
+  io.cls = cls; io.loc = loc; io.mask = mask; io.best = best_idx; io.pos = pos; io.rec = records;
+  io.refine = refine_out; io.mask_col = mask_col;
+  e->impl->do_step(slot0, B, io, static_cast<cudaStream_t>(stream));
+  SM_API_END
+}
+
+int sm_step_host_async(sm_engine* e, int32_t slot0, int32_t B, const sm_step_io* io, void* stream, int32_t* ticket) {
+  SM_API_BEGIN
+  SMK_CHECK(e && io && ticket, "null argument");
+  *ticket = e->impl->step_host_async(slot0, B, *io, static_cast<cudaStream_t>(stream));
+  SM_API_END
+}
+
 int sm_xcorr_depthwise(const float* x, const float* k, float* out, int32_t B, int32_t C, int32_t H, int32_t W, int32_t kh,
                        int32_t kw, void* stream) {
   SM_API_BEGIN
@@ -1440,7 +1633,7 @@ int sm_warp_affine(const float* src, int32_t src_h, int32_t src_w, const double*
 }
 
 int sm_select(sm_engine* e, int32_t B, const float* cls, const float* loc, const float* anchors, const float* window,
-              const float* target_sz_in_crop, double penalty_k, double window_influence, int32_t* best_idx, int32_t* pos,
+              const double* target_sz_in_crop, double penalty_k, double window_influence, int32_t* best_idx, int32_t* pos,
               float* records, void* stream) {
   SM_API_BEGIN
   SMK_CHECK(e && cls && loc && anchors && window && target_sz_in_crop && best_idx && pos && records, "null argument");

@@ -327,7 +327,8 @@ __global__ void xcorr_nchw_generic_kernel(const float* __restrict__ x, const flo
 // ------------------------------------------------------------------------------------------------
 // ResDownS crop x[:, :, 4:-4, 4:-4] (custom.py:21-24) and the refine-stage windows
 // pad(f, P)[scale*dy : scale*dy+size, scale*dx : ...] (custom.py:133-135), zero outside the feature map.
-__global__ void crop_kernel(Act in, Act out, const int32_t* __restrict__ pos, int scale, int padv, int fixed_off) {
+__global__ void crop_kernel(Act in, Act out, const int32_t* __restrict__ pos, int scale, int padv, int fixed_off,
+                            int pos_max) {
   const size_t total = out.numel() / 8;   // 8 halfs (16 B) per thread
   const int c8n = out.C / 8;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -336,9 +337,9 @@ __global__ void crop_kernel(Act in, Act out, const int32_t* __restrict__ pos, in
     const int xo = m % out.W, yo = (m / out.W) % out.H;
     const int b = m / ((size_t)out.W * out.H);
     int yi, xi;
-    if (pos != nullptr) {
-      yi = scale * pos[2 * b] + yo - padv;
-      xi = scale * pos[2 * b + 1] + xo - padv;
+    if (pos != nullptr) {       // positions are clamped to the response map: a bad (dy,dx) must not read out of bounds
+      yi = scale * min(max(pos[2 * b], 0), pos_max) + yo - padv;
+      xi = scale * min(max(pos[2 * b + 1], 0), pos_max) + xo - padv;
     } else {
       yi = yo + fixed_off;
       xi = xo + fixed_off;
@@ -358,9 +359,18 @@ __global__ void crop_kernel(Act in, Act out, const int32_t* __restrict__ pos, in
 // p3 = corr_feature[b, :, dy, dx] (custom.py:144-145) as fp32 [B][C]
 __global__ void gather_corr_kernel(Act corr, const int32_t* __restrict__ pos, float* __restrict__ out) {
   const int b = blockIdx.x;
-  const int dy = pos[2 * b], dx = pos[2 * b + 1];
+  const int dy = min(max(pos[2 * b], 0), corr.H - 1), dx = min(max(pos[2 * b + 1], 0), corr.W - 1);
   for (int c = threadIdx.x; c < corr.C; c += blockDim.x)
     out[(size_t)b * corr.C + c] = split_load(corr.hi, corr.lo, (((size_t)b * corr.H + dy) * corr.W + dx) * corr.C + c);
+}
+
+// mask[b, :, dy, dx] of the raw 63*63-channel mask head output (tools/test.py:259-260, the non-refine branch)
+__global__ void gather_mask_col_kernel(const float* __restrict__ mask, const int32_t* __restrict__ pos, int C, int R,
+                                       float* __restrict__ out) {
+  const int b = blockIdx.x;
+  const int dy = min(max(pos[2 * b], 0), R - 1), dx = min(max(pos[2 * b + 1], 0), R - 1);
+  const float* src = mask + (size_t)b * C * R * R + (size_t)dy * R + dx;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) out[(size_t)b * C + c] = src[(size_t)c * R * R];
 }
 
 // ConvTranspose2d(256, 32, 15, 15) on a 1x1 input (custom.py:120,149) == [B x Cin] x [Cin x N] + bias,
@@ -506,12 +516,14 @@ __global__ void __launch_bounds__(256) small_conv3x3_kernel(const float* __restr
 //   pscore = penalty*score*(1-wi) + window*wi (:235-236); argmax (:237, first maximum wins like np.argmax);
 //   (dy, dx) = unravel(best, (A, R, R))[1:] (:253-254).
 // cls f32 [B][2A][R][R], loc f32 [B][4A][R][R], anchors f32 [A*R*R][4] (cx,cy,w,h), window f32 [A*R*R],
-// tsz f32 [B][2] = target_sz * scale_x.  The network part is fp32 as in the reference; the penalty is
-// evaluated in fp64 (numpy promotes those expressions to float64 through the float64 target size).
+// tsz f64 [B][2] = target_sz * scale_x (float64 as in the reference).  The network part is fp32 as in the reference;
+// the penalty is evaluated in fp64 (numpy promotes those expressions to float64 through the float64 target size).
+// np.argmax semantics incl. NaN: the first NaN wins over every number (a NaN/Inf network output or a 0/0 target
+// size must not leave `besti` unset: rec/pos are always in range).  rec[7] = best index (exact in fp32).
 __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ cls, const float* __restrict__ loc,
                                                      const float* __restrict__ anchors,
                                                      const float* __restrict__ window,
-                                                     const float* __restrict__ tsz, int A, int R, double penalty_k,
+                                                     const double* __restrict__ tsz, int A, int R, double penalty_k,
                                                      double window_influence, int32_t* __restrict__ best_idx,
                                                      int32_t* __restrict__ pos, float* __restrict__ rec) {
   const int b = blockIdx.x;
@@ -522,8 +534,15 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ c
   const double tpad = (tw + th) * 0.5;
   const double tsz_c = sqrt((tw + tpad) * (th + tpad));
   const double tratio = tw / th;
+  // candidate order: (is NaN, value, -index) — NaN beats every number, ties go to the lower index
   double best = -INFINITY;
   int besti = 0x7fffffff;
+  int bestnan = -1;                 // -1: no candidate yet
+  auto better = [](int nan_a, double va, int ia, int nan_b, double vb, int ib) {
+    if (nan_a != nan_b) return nan_a > nan_b;
+    if (nan_a == 1) return ia < ib;
+    return va > vb || (va == vb && ia < ib);
+  };
   for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
     const int a = idx / RR, p = idx - a * RR;
     const float s0 = c[(size_t)a * RR + p], s1 = c[(size_t)(A + a) * RR + p];
@@ -541,23 +560,27 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ c
     rc = fmax(rc, 1.0 / rc);
     const double penalty = exp(-(rc * sc - 1.0) * penalty_k);
     const double ps = penalty * (double)score * (1.0 - window_influence) + (double)window[idx] * window_influence;
-    if (ps > best || (ps == best && idx < besti)) { best = ps; besti = idx; }
+    const int isn = ps != ps ? 1 : 0;
+    if (better(isn, ps, idx, bestnan, best, besti)) { best = ps; besti = idx; bestnan = isn; }
   }
   __shared__ double sv[256];
   __shared__ int si[256];
+  __shared__ int sn[256];
   sv[threadIdx.x] = best;
   si[threadIdx.x] = besti;
+  sn[threadIdx.x] = bestnan;
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
     if (threadIdx.x < s) {
-      const double ov = sv[threadIdx.x + s];
-      const int oi = si[threadIdx.x + s];
-      if (ov > sv[threadIdx.x] || (ov == sv[threadIdx.x] && oi < si[threadIdx.x])) { sv[threadIdx.x] = ov; si[threadIdx.x] = oi; }
+      if (better(sn[threadIdx.x + s], sv[threadIdx.x + s], si[threadIdx.x + s], sn[threadIdx.x], sv[threadIdx.x],
+                 si[threadIdx.x])) {
+        sv[threadIdx.x] = sv[threadIdx.x + s]; si[threadIdx.x] = si[threadIdx.x + s]; sn[threadIdx.x] = sn[threadIdx.x + s];
+      }
     }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const int idx = si[0];
+    const int idx = min(max(si[0], 0), n - 1);
     const int a = idx / RR, p = idx - a * RR;
     best_idx[b] = idx;
     pos[2 * b] = p / R;          // delta_y
@@ -582,7 +605,7 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ c
     o[4] = score;
     o[5] = (float)exp(-(rc * sc - 1.0) * penalty_k);
     o[6] = (float)sv[0];
-    o[7] = 0.f;
+    o[7] = (float)idx;
   }
 }
 
@@ -770,9 +793,19 @@ small_conv3x3_tiled_kernel(const float* __restrict__ a, const float* __restrict_
   }
 }
 
+// SM count of the current device (grids of the grid-stride / persistent kernels are sized from it)
+inline int device_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int& c = cached[dev & 63];
+  if (c == 0 && cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) c = 148;
+  return c;
+}
 inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
-  return (int)(g > 148 * 64 ? 148 * 64 : (g == 0 ? 1 : g));
+  const size_t cap = (size_t)device_sms() * 64;
+  return (int)(g > cap ? cap : (g == 0 ? 1 : g));
 }
 
 }  // namespace
@@ -837,18 +870,24 @@ void launch_xcorr_nchw_f32(const float* x, const float* k, float* out, int plane
 
 void launch_crop_center(const Act& in, int crop, Act out, cudaStream_t st) {
   SMK_CHECK(out.H == in.H - 2 * crop && out.C == in.C && in.C % 8 == 0, "crop shapes");
-  crop_kernel<<<grid_for(out.numel() / 8, 256), 256, 0, st>>>(in, out, nullptr, 0, 0, crop);
+  crop_kernel<<<grid_for(out.numel() / 8, 256), 256, 0, st>>>(in, out, nullptr, 0, 0, crop, 0);
   SMK_CUDA(cudaGetLastError());
 }
 
-void launch_refine_crop(const Act& in, const int32_t* pos, int scale, int padv, int size, Act out, cudaStream_t st) {
+void launch_refine_crop(const Act& in, const int32_t* pos, int pos_max, int scale, int padv, int size, Act out,
+                        cudaStream_t st) {
   SMK_CHECK(out.H == size && out.W == size && out.C == in.C && in.C % 8 == 0, "refine crop shapes");
-  crop_kernel<<<grid_for(out.numel() / 8, 256), 256, 0, st>>>(in, out, pos, scale, padv, 0);
+  crop_kernel<<<grid_for(out.numel() / 8, 256), 256, 0, st>>>(in, out, pos, scale, padv, 0, pos_max);
   SMK_CUDA(cudaGetLastError());
 }
 
 void launch_gather_corr(const Act& corr, const int32_t* pos, float* out, cudaStream_t st) {
   gather_corr_kernel<<<corr.B, 256, 0, st>>>(corr, pos, out);
+  SMK_CUDA(cudaGetLastError());
+}
+
+void launch_gather_mask_col(const float* mask, const int32_t* pos, int B, int C, int R, float* out, cudaStream_t st) {
+  gather_mask_col_kernel<<<B, 256, 0, st>>>(mask, pos, C, R, out);
   SMK_CUDA(cudaGetLastError());
 }
 
@@ -876,7 +915,7 @@ void launch_warp_affine(const float* src, int sh, int sw, const double* maps, fl
   SMK_CUDA(cudaGetLastError());
 }
 
-void launch_select(const float* cls, const float* loc, const float* anchors, const float* window, const float* tsz,
+void launch_select(const float* cls, const float* loc, const float* anchors, const float* window, const double* tsz,
                    int B, int A, int R, double penalty_k, double window_influence, int32_t* best_idx, int32_t* pos,
                    float* rec, cudaStream_t st) {
   select_kernel<<<B, 256, 0, st>>>(cls, loc, anchors, window, tsz, A, R, penalty_k, window_influence, best_idx, pos, rec);
@@ -910,7 +949,7 @@ void launch_small_conv3x3_maps(const float* a, const float* b, int B, int Hi, in
   if (Cin == CI && Cout == CO) {                                                                                 \
     const size_t threads = M * (CO / CPT);                                                                       \
     size_t blocks = (threads + 255) / 256;                                                                       \
-    if (blocks > 148 * 6) blocks = 148 * 6;                                                                      \
+    if (blocks > (size_t)device_sms() * 6) blocks = (size_t)device_sms() * 6;                                                                     \
     small_conv3x3_kernel<CI, CO, CPT><<<(unsigned)blocks, 256, 0, st>>>(a, b, B, Hi, Wi, Ho, Wo, ymap, xmap, w,  \
                                                                           bias, relu, out);                      \
     launched = true;                                                                                             \
@@ -923,7 +962,7 @@ void launch_small_conv3x3_maps(const float* a, const float* b, int B, int Hi, in
     static unsigned long long attr = 0;                                                                          \
     ensure_dynamic_smem(small_conv3x3_tiled_kernel<CI, CO, CPT>, SMEM, attr);                                    \
     const int tiles = B * ((Ho + SCT_H - 1) / SCT_H) * ((Wo + SCT_W - 1) / SCT_W);                               \
-    const int blocks = tiles < 148 * 2 ? tiles : 148 * 2;                                                        \
+    const int blocks = tiles < device_sms() * 2 ? tiles : device_sms() * 2;                                                       \
     small_conv3x3_tiled_kernel<CI, CO, CPT><<<blocks, NT, SMEM, st>>>(a, b, B, Hi, Wi, Ho, Wo, ymap, xmap, w,    \
                                                                        bias, relu, out);                         \
     launched = true;                                                                                             \

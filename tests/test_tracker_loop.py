@@ -1,4 +1,4 @@
-"""The tracker loop around the hot path: the product's host restatement (siammask_b200/tracker.py)
+"""The tracker loop around the hot path: the host restatement of the reference loop (oracle/ref_loop.py)
 against the golden trajectory produced by the reference's OWN loop (tools/test.py siamese_init/siamese_track,
 oracle/make_golden.py::tracker_loop_golden), first driven by the CPU oracle network (tight), then — on the GPU —
 by the CUDA engine with the on-device score/box post-processing `sm_select` (network parity tolerance)."""
@@ -11,7 +11,7 @@ import torch
 from conftest import GOLDEN
 from oracle.siammask_oracle import Oracle
 from oracle.synthetic_video import make_frames
-from siammask_b200 import tracker
+from oracle import ref_loop as tracker
 
 HP = {"instance_size": 255, "base_size": 8, "out_size": 127, "seg_thr": 0.35, "penalty_k": 0.04,
       "window_influence": 0.4, "lr": 1.0}
@@ -34,7 +34,12 @@ def _run(net, device):
 
 
 def test_generate_anchor_layout():
-    a = tracker.generate_anchor({"stride": 8, "ratios": [0.33, 0.5, 1, 2, 3], "scales": [8], "round_dight": 0}, 25)
+    from siammask_b200 import anchors
+    cfg = {"stride": 8, "ratios": [0.33, 0.5, 1, 2, 3], "scales": [8], "round_dight": 0}
+    for R in (25, 41):       # the product's table == the restatement of tools/test.py:113-129
+        assert np.array_equal(anchors.generate_anchor(cfg, R), tracker.generate_anchor(cfg, R))
+    assert np.array_equal(anchors.cosine_window(25, 5), np.tile(np.outer(np.hanning(25), np.hanning(25)).flatten(), 5))
+    a = anchors.generate_anchor({"stride": 8, "ratios": [0.33, 0.5, 1, 2, 3], "scales": [8], "round_dight": 0}, 25)
     assert a.shape == (5 * 25 * 25, 4) and a.dtype == np.float32
     # order (anchor, y, x); centres on a stride-8 grid centred at 0; sizes from int(sqrt(64/r)) * 8
     assert tuple(a[0]) == (-96.0, -96.0, 104.0, 32.0)
@@ -64,12 +69,12 @@ def test_device_select_matches_numpy(calib_sd):
     window = np.tile(np.outer(np.hanning(25), np.hanning(25)).flatten(), 5)
     tsz = np.array([[60.0, 40.0], [35.5, 80.25], [100.0, 100.0]])
     best, pos, rec = m.select(cls, loc, torch.from_numpy(anchor), torch.from_numpy(window.astype(np.float32)),
-                              torch.from_numpy(tsz).float(), 0.04, 0.4)
+                              torch.from_numpy(tsz), 0.04, 0.4)
     best, pos, rec = best.cpu().numpy(), pos.cpu().numpy(), rec.cpu().numpy()
     for b in range(3):
         bid, box, score, pen, ps = tracker.select_numpy(cls[b:b + 1].cpu(), loc[b:b + 1].cpu(), anchor, window, tsz[b],
                                                         0.04, 0.4)
-        assert best[b] == bid
+        assert best[b] == bid and int(rec[b, 7]) == bid
         assert tuple(pos[b]) == tuple(np.unravel_index(bid, (5, 25, 25))[1:])
         np.testing.assert_allclose(rec[b, :4], box, rtol=2e-5, atol=1e-4)
         np.testing.assert_allclose(rec[b, 4:7], [score, pen, ps], rtol=2e-5, atol=1e-6)
