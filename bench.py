@@ -3,36 +3,44 @@
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+    python bench.py --config {2,3,5} ...                     # BASELINE.json configs[1..4] presets (default: 2 -> configs[1])
 
-One "step" = one pass of the hot path over one batch of synthetic search regions:
-`track_mask` (backbone -> depthwise xcorr -> cls/loc/mask heads) + `track_refine` for B=64 paired tracker
-streams per GPU (BASELINE.json configs[1]: "batch=64 synthetic search regions, 1xB200, full track() path with
-mask refine"); templates are cached per slot (configs[3]).  N>1: one process per GPU (torchrun), streams are
-sharded, the packed weights are broadcast ONCE over NCCL at init, no per-frame collective ("weak" scaling).
+One "step" = one pass of the hot path over one batch of synthetic search regions — the whole frame of
+`siamese_track` (tools/test.py:201-261): `track_mask` (backbone -> depthwise xcorr -> cls/loc/mask heads) ->
+score/box post-processing + argmax ON THE DEVICE -> `track_refine` at the selected position, for B paired tracker
+streams per GPU (BASELINE.json configs[1]: "batch=64 synthetic search regions, 1xB200, full track() path with mask
+refine"); templates are cached per slot (configs[3]).  N>1: one process per GPU (torchrun), streams are sharded, the
+packed weights are broadcast ONCE over NCCL at init, no per-frame collective ("weak" scaling).
 
-Prints ONE JSON line (rank 0).  `value` = whole-job frames/s with inputs resident in HBM; `e2e` = the same
-metric through the C-ABI host-buffer call (H2D of every frame + D2H of cls/loc/mask logits inside the timed
-region); `roofline` = the tensor-core conv family (dominant kernel) timed per launch with CUDA events;
-`cpu_baseline` = the oracle port of the reference timed on this box's host cores.
+Prints ONE JSON line (rank 0).  `value` = whole-job frames/s with inputs resident in HBM (C ABI `sm_step`); `e2e` =
+the same frame through the host-buffer call `sm_step_host_async` (H2D of every frame + target sizes, D2H of the
+records and refine logits inside the timed region, SAME flags as `value`); `roofline` = the tensor-core conv family
+(dominant kernel) timed per launch with CUDA events; `cpu_baseline` = the oracle port of the reference timed on all of
+this box's host cores; `parity_check` = max relative error of this run's outputs against the CPU oracle.
+The timed region is at least --min-seconds long (default 2 s): every reported step is repeated `passes_per_step`
+times inside it and all per-step figures are per pass.
 """
 from __future__ import annotations
 
 import argparse
 import json
-
-import numpy as np
+import math
 import os
 import statistics
 import subprocess
 import sys
 import time
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "search-region frames/sec (127/255 SiamMask-sharp)"
-GFLOP_PER_FRAME = {255: 33.915, 383: 77.938}          # BASELINE.md §2 (algorithmic, conv_kernel cached)
+GFLOP_SHARP = {255: 33.915, 383: 77.938}              # BASELINE.md §2 (algorithmic, conv_kernel cached)
+GFLOP_RPN = {255: 30.811, 383: 71.139}
 XCORR_BYTES = {255: 1526784, 383: 3820544}            # per branch per frame, fp32 algorithmic (BASELINE.md §2)
+PENALTY_K, WINDOW_INFLUENCE = 0.04, 0.4               # config_davis.json hp
 
 
 def load_peaks():
@@ -94,103 +102,196 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples inside the timed region"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        bad = reasons & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        stuck = statistics.median(sm) < 0.6 * max(mx) and not reasons
+        return {"sm_mhz": statistics.median(sm), "sm_min_mhz": min(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons), "rejected": bool(bad or stuck)}
 
 
 # ---------------------------------------------------------------------------------------------------
-def run_reference(args, rank):
-    """The reference algorithm on the host CPU: the oracle port (oracle/siammask_oracle.py), all host threads."""
-    if rank != 0:
-        return
+# the reference's CPU implementation of the path (oracle port), on ALL host cores
+def _cpu_worker(args):
+    """One CPU worker process: B=`ref_batch` paired frames per step, `threads` torch threads.  Waits for the common
+    start time, then runs for `seconds` (or `steps` steps) and prints {"frames": n, "seconds": dt}."""
     import torch
     from oracle.siammask_oracle import Oracle
     from siammask_b200.checkpoint import synthetic_state_dict
-    sd = synthetic_state_dict(0)
+    torch.set_num_threads(args.threads)
+    sd = synthetic_state_dict(0, mask=not args.rpn_only, refine=not args.rpn_only)
     bs = args.ref_batch
-    g = torch.Generator().manual_seed(1)
+    g = torch.Generator().manual_seed(1 + args.worker_id)
     z = torch.rand(bs, 3, 127, 127, generator=g) * 255
     xs = [torch.rand(bs, 3, args.search, args.search, generator=g) * 255 for _ in range(2)]
-    pos = torch.randint(0, 25, (bs, 2), generator=g).numpy()
     o = Oracle(sd)
     o.template(z)
 
     def step(i):
-        o.track_mask(xs[i % 2])
-        o.track_refine(pos)
-    cores = pick_threads(lambda: step(0), torch)
-    for i in range(args.warmup):
+        if args.rpn_only:
+            o.track(xs[i % 2])
+        else:
+            o.track_mask(xs[i % 2])
+            o.track_refine((12, 12))
+    for i in range(max(1, args.warmup)):
         step(i)
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step(i)
+    print("READY", flush=True)
+    sys.stdin.readline()                      # the parent releases all workers together
+    n, t0 = 0, time.perf_counter()
+    if args.worker_seconds > 0:
+        while time.perf_counter() - t0 < args.worker_seconds:
+            step(n); n += 1
+    else:
+        for i in range(args.steps):
+            step(i); n += 1
     dt = time.perf_counter() - t0
-    fps = bs * args.steps / dt
-    sample = (f"{args.steps} steps x {bs} paired frames, track_mask+track_refine, torch CPU fp32, {cores} threads "
-              f"(fastest of 8/16/32/64/all {os.cpu_count()})")
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, bs, 1),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    print(json.dumps({"frames": n * bs, "seconds": dt, "steps": n}), flush=True)
 
 
-def workload_config(args, batch_per_gpu, world):
-    return {"workload": f"SiamMask-sharp config_davis, template 127 / search {args.search}, response "
-                        f"{(args.search - 127) // 8 + 9}x{(args.search - 127) // 8 + 9}: track_mask (incl. 256->3969 "
-                        f"mask head) + on-device score/box selection + track_refine at the selected position, {batch_per_gpu} paired streams per GPU, templates cached per slot",
-            "global_batch": batch_per_gpu * world, "batch_per_gpu": batch_per_gpu, "search": args.search,
-            "parallelism": f"streams sharded over {world} GPU(s), one NCCL weight broadcast at init, "
-                           "no per-frame collective; inside a GPU the batch runs as two concurrent lanes of "
-                           "batch_per_gpu/2 streams (batches >= 16)",
-            "l2": "inputs rotate over 4 device buffers (4 x 50 MB) and every step streams > 5 GB of activations "
-                  "(>> 126 MB L2)"}
-
-
-def pick_threads(fn, torch):
-    """torch's CPU convs stop scaling (and collapse) well before 100+ threads at batch 1: try a few thread
-    counts for ~1 s each and keep the fastest, so the CPU baseline is the best the host can do."""
-    ncpu = os.cpu_count() or 1
-    best, best_t = 1, float("inf")
-    for n in sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu}):
-        torch.set_num_threads(n)
-        fn()
-        t0 = time.perf_counter()
-        fn()
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = n, dt
-        if dt > 3.0:
-            break
-    torch.set_num_threads(best)
-    return best
-
-
-def cpu_baseline(args, seconds=10.0):
+def pick_threads(args):
+    """torch's CPU convs stop scaling (and collapse) well before 100+ threads at small batch: time one worker at a
+    few thread counts and keep the one with the best frames/s PER THREAD-SECOND budget, i.e. the count at which
+    floor(cpus / threads) concurrent workers deliver the most whole-host throughput."""
     import torch
     from oracle.siammask_oracle import Oracle
     from siammask_b200.checkpoint import synthetic_state_dict
-    sd = synthetic_state_dict(0)
+    ncpu = os.cpu_count() or 1
+    sd = synthetic_state_dict(0, mask=not args.rpn_only, refine=not args.rpn_only)
     g = torch.Generator().manual_seed(1)
-    z = torch.rand(1, 3, 127, 127, generator=g) * 255
-    x = torch.rand(1, 3, args.search, args.search, generator=g) * 255
+    bs = args.ref_batch
+    z = torch.rand(bs, 3, 127, 127, generator=g) * 255
+    x = torch.rand(bs, 3, args.search, args.search, generator=g) * 255
     o = Oracle(sd)
     o.template(z)
 
     def one():
-        o.track_mask(x); o.track_refine((12, 12))
-    cores = pick_threads(one, torch)
-    n, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < seconds:
-        o.track_mask(x); o.track_refine((12, 12))
-        n += 1
-    dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "frames/s", "cores": cores, "host_cpus": os.cpu_count(), "kind": "port",
-            "sample": f"{n} frames, B=1 track_mask+track_refine((12,12)), oracle port (torch CPU fp32, "
-                      f"{cores} threads = fastest of 8/16/32/64/all), {dt:.1f} s"}
+        if args.rpn_only:
+            o.track(x)
+        else:
+            o.track_mask(x); o.track_refine((12, 12))
+    best, best_rate = 1, 0.0
+    for n in sorted({c for c in (4, 8, 16, 32) if c <= ncpu} | ({ncpu} if ncpu <= 8 else set())):
+        torch.set_num_threads(n)
+        one()
+        t0 = time.perf_counter()
+        one()
+        dt = time.perf_counter() - t0
+        rate = (ncpu // n) * bs / dt              # projected whole-host frames/s with cpus // n such workers
+        if rate > best_rate:
+            best, best_rate = n, rate
+    return best
+
+
+def run_cpu_fleet(args, seconds=0.0, steps=0):
+    """floor(cpus / threads) concurrent worker processes x `threads` torch threads each — the path shards over
+    independent streams on the CPU exactly as it does over GPUs.  Returns (frames/s, cores used, description)."""
+    ncpu = os.cpu_count() or 1
+    threads = args.cpu_threads if args.cpu_threads > 0 else pick_threads(args)
+    nproc = max(1, ncpu // threads)
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads))
+    procs = []
+    for w in range(nproc):
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "_cpu_worker", "--threads", str(threads),
+               "--worker-id", str(w), "--worker-seconds", str(seconds), "--steps", str(steps), "--warmup",
+               str(args.warmup), "--search", str(args.search), "--ref-batch", str(args.ref_batch)]
+        if args.rpn_only:
+            cmd.append("--rpn-only")
+        procs.append(subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, env=env))
+    for p in procs:
+        line = p.stdout.readline()
+        if "READY" not in line:
+            raise RuntimeError("cpu worker failed to start: " + line)
+    t0 = time.perf_counter()
+    for p in procs:
+        p.stdin.write("go\n"); p.stdin.flush()
+    frames, longest = 0, 0.0
+    for p in procs:
+        rec = json.loads(p.stdout.readline())
+        frames += rec["frames"]; longest = max(longest, rec["seconds"])
+        p.wait(30)
+    wall = time.perf_counter() - t0
+    dt = max(longest, 1e-9)
+    what = "track" if args.rpn_only else "track_mask+track_refine"
+    sample = (f"{nproc} worker processes x {threads} torch threads (of {ncpu} host CPUs), each B={args.ref_batch} paired "
+              f"frames per step, {what}, oracle port (torch CPU fp32), {frames} frames in {dt:.1f} s (wall {wall:.1f} s)")
+    return frames / dt, nproc * threads, sample, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    fps, cores, sample, dt = run_cpu_fleet(args, steps=args.steps)
+    print(json.dumps({
+        "impl": "reference", "metric": metric_name(args), "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.batch, max(1, args.gpus)),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "host_cpus": os.cpu_count(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def metric_name(args):
+    return METRIC.replace("SiamMask-sharp", "SiamRPN-only") if args.rpn_only else METRIC.replace("255", str(args.search))
+
+
+def workload_config(args, batch_per_gpu, world):
+    R = (args.search - 127) // 8 + 9
+    if args.rpn_only:
+        what = "SiamRPN-only (experiments/siamrpn_resnet): track -> cls/loc + on-device score/box selection"
+    else:
+        what = ("SiamMask-sharp config_davis: track_mask (incl. 256->3969 mask head) + on-device score/box selection + "
+                "track_refine at the selected position")
+    return {"workload": f"{what}; template 127 / search {args.search}, response {R}x{R}, {batch_per_gpu} paired streams "
+                        f"per GPU, templates cached per slot (BASELINE.json configs[{args.config - 1}])",
+            "global_batch": batch_per_gpu * world, "batch_per_gpu": batch_per_gpu, "search": args.search,
+            "parallelism": f"streams sharded over {world} GPU(s), one NCCL weight broadcast at init, "
+                           "no per-frame collective; inside a GPU the batch runs as two concurrent lanes of "
+                           "batch_per_gpu/2 streams (batches >= 16)",
+            "l2": "inputs rotate over 4 device buffers (4 x 50 MB at B=64) and every step streams > 5 GB of "
+                  "activations (>> 126 MB L2)"}
+
+
+# ---------------------------------------------------------------------------------------------------
+def cudnn_context(args, dev, seconds=1.5):
+    """The de-facto 'existing Blackwell implementation' (SURVEY §2.3, §8d): the same network in PyTorch on this GPU
+    (cuDNN/cuBLAS), fp32 strict and TF32 allowed, B=1 and the bench batch.  Context only — not the product path."""
+    import torch
+    from oracle.siammask_oracle import Oracle
+    from siammask_b200.checkpoint import synthetic_state_dict
+    sd = {k: v.to(dev) for k, v in synthetic_state_dict(0, mask=not args.rpn_only, refine=not args.rpn_only).items()}
+    out = {}
+    for tf32 in (False, True):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        for bs in (1, args.batch):
+            try:
+                g = torch.Generator(device=dev).manual_seed(5)
+                o = Oracle(sd)
+                o.template(torch.rand(bs, 3, 127, 127, device=dev, generator=g) * 255)
+                x = torch.rand(bs, 3, args.search, args.search, device=dev, generator=g) * 255
+
+                def one():
+                    if args.rpn_only:
+                        o.track(x)
+                    else:
+                        o.track_mask(x); o.track_refine((12, 12))
+                for _ in range(3):
+                    one()
+                torch.cuda.synchronize(dev)
+                n, t0 = 0, time.perf_counter()
+                while time.perf_counter() - t0 < seconds:
+                    one(); n += 1
+                    torch.cuda.synchronize(dev)
+                dt = time.perf_counter() - t0
+                out[f"{'tf32' if tf32 else 'fp32'}_b{bs}"] = round(n * bs / dt, 1)
+                del o, x
+            except Exception as exc:                       # context only: never fail the bench on it
+                out[f"{'tf32' if tf32 else 'fp32'}_b{bs}"] = f"failed: {type(exc).__name__}"
+            torch.cuda.empty_cache()
+    torch.backends.cudnn.allow_tf32 = True
+    out["what"] = ("oracle port (torch functional restatement of the reference model) on this GPU via cuDNN/cuBLAS, "
+                   "frames/s, shared refine position, eager mode")
+    return out
 
 
 def run_gpu(args, rank, local_rank, world):
@@ -198,7 +299,7 @@ def run_gpu(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
     import siammask_b200 as smb
-    from siammask_b200 import _lib
+    from siammask_b200 import _lib, anchors as anc
     from siammask_b200.parallel import broadcast_weights, max_over_ranks, shard_streams
 
     torch.cuda.set_device(local_rank)
@@ -206,13 +307,18 @@ def run_gpu(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     S = args.search
+    sharp = not args.rpn_only
     # weak scaling: args.batch streams per GPU; this rank owns a contiguous block of the global stream ids
     B = len(shard_streams(args.batch * world, world, rank))
     R = (S - 127) // 8 + 9
-    m = smb.Custom(anchors=smb.DEFAULT_ANCHORS, search_size=S, max_batch=B, num_slots=B, precision=args.precision,
-                   mask=not args.rpn_only)
+    A = 5
+    # two independent groups of B streams (slots [0,B) and [B,2B)) so the host-buffer pipeline can keep one step in
+    # flight without pretending that frame k+1 of a tracker is available before frame k is finished
+    m = smb.Custom(anchors=smb.DEFAULT_ANCHORS, search_size=S, max_batch=B, num_slots=2 * B, precision=args.precision,
+                   mask=sharp)
+    sd = smb.synthetic_state_dict(0, mask=sharp, refine=sharp)
     if rank == 0:
-        m.load_state_dict(smb.synthetic_state_dict(0, mask=not args.rpn_only, refine=not args.rpn_only))
+        m.load_state_dict(sd)
     m.eval().to(dev)
     if world > 1:                       # the one collective of the whole job: weights, once, at init
         broadcast_weights(m.weight_blob(), src=0)
@@ -222,27 +328,17 @@ def run_gpu(args, rank, local_rank, world):
     gen = torch.Generator(device=dev).manual_seed(100 + rank)
     z = torch.rand(B, 3, 127, 127, device=dev, generator=gen) * 255
     xs = [torch.rand(B, 3, S, S, device=dev, generator=gen) * 255 for _ in range(4)]
-    pos = torch.randint(0, R, (B, 2), device=dev, generator=gen, dtype=torch.int32)
     # what siamese_init prepares per stream (tools/test.py:142-161): anchors, cosine window, target size in the crop
-    from siammask_b200 import tracker
-    anchors_dev = torch.from_numpy(tracker.generate_anchor(smb.DEFAULT_ANCHORS, R)).to(dev)
-    window_dev = torch.from_numpy(np.tile(np.outer(np.hanning(R), np.hanning(R)).flatten(), 5).astype(np.float32)).to(dev)
-    tsz_dev = torch.rand(B, 2, device=dev, generator=gen) * 60 + 30
-    m.template(z)
-
-    def step_rpn(i, mask_head=True):
-        cls, loc = m.track(xs[i % 4])
-        return m.select(cls, loc, anchors_dev, window_dev, tsz_dev, 0.04, 0.4)
+    anchors_dev = torch.from_numpy(anc.generate_anchor(smb.DEFAULT_ANCHORS, R)).to(dev)
+    window_dev = torch.from_numpy(anc.cosine_window(R, A).astype(np.float32)).to(dev)
+    tsz_dev = (torch.rand(B, 2, device=dev, generator=gen) * 60 + 30).double()
+    m.template(z, slot0=0)
+    m.template(z, slot0=B)
 
     def step(i, mask_head=True):
-        if args.rpn_only:
-            return step_rpn(i)
-        # the full per-frame path of siamese_track (tools/test.py:201-261) without leaving the device:
-        # track_mask -> score/box post-processing + argmax -> track_refine at the selected position
-        cls, loc, mask = m.track_mask(xs[i % 4], mask_head=mask_head)
-        best, sel_pos, rec = m.select(cls, loc, anchors_dev, window_dev, tsz_dev, 0.04, 0.4)
-        ref = m.track_refine(sel_pos)
-        return (cls, loc, mask, rec), ref
+        # the whole frame of siamese_track (tools/test.py:201-261) in one engine call, nothing leaves the device
+        return m.step(xs[i % 4], anchors_dev, window_dev, tsz_dev, PENALTY_K, WINDOW_INFLUENCE, refine=sharp,
+                      mask_head=sharp and mask_head)
 
     def barrier():
         torch.cuda.synchronize()
@@ -250,78 +346,108 @@ def run_gpu(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, n):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(steps):
+        for i in range(n):
             fn(i)
         e1.record()
         barrier()
         return max_over_ranks(e0.elapsed_time(e1), device=dev)
 
     sampler = ClockSampler("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
-    for i in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for i in range(warm):
         step(i)
+    # size the timed region: at least --min-seconds, every reported step = `passes` passes over a batch
+    est_ms = timed(step, 3) / 3
+    passes = max(1, math.ceil(args.min_seconds * 1e3 / (est_ms * args.steps)))
+    if world > 1:
+        t = torch.tensor([passes], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        passes = int(t.item())
+    n_pass = args.steps * passes
     l0 = m.launch_count
     t_start = time.perf_counter()
-    ms = timed(step, args.steps)
+    ms = timed(step, n_pass)
     t_end = time.perf_counter()
     launches = m.launch_count - l0
     clocks = sampler.stop(t_start, t_end) if sampler else None
-    fps = world * B * args.steps / (ms * 1e-3)
-    ms_skip = timed(lambda i: step(i, mask_head=False), args.steps)
-    fps_skip = world * B * args.steps / (ms_skip * 1e-3)
+    fps = world * B * n_pass / (ms * 1e-3)
+    fps_skip = None
+    if sharp:
+        n_skip = max(3, n_pass // 4)
+        ms_skip = timed(lambda i: step(i, mask_head=False), n_skip)
+        fps_skip = world * B * n_skip / (ms_skip * 1e-3)
 
-    if args.rpn_only:
-        if rank == 0:
-            gfl = {255: 30.811, 383: 71.139}.get(S, 0.0)
-            print(json.dumps({"metric": METRIC.replace("SiamMask-sharp", "SiamRPN-only"), "value": fps, "unit": "frames/s",
-                              "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                              "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                              "vs_baseline": None, "precision_mode": args.precision, "data": "synthetic",
-                              "config": {"workload": f"SiamRPN-only track + on-device selection, search {S}, {B} streams/GPU"},
-                              "algorithmic_tflops": fps * gfl / 1e3, "gpu_launches": launches, "clocks": clocks}))
+    # ---- parity of THIS run's outputs against the CPU oracle (first and last stream of this rank)
+    parity = None
+    if args.verify:
+        parity = verify_against_oracle(args, m, sd, z, xs[1], anchors_dev, window_dev, tsz_dev, B, dev, sharp)
         if world > 1:
-            dist.destroy_process_group()
-        return
+            t = torch.tensor([parity["max_rel"]], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            worst = float(t.item())
+            t2 = torch.tensor([1.0 if parity["argmax_equal"] else 0.0], device=dev)
+            dist.all_reduce(t2, op=dist.ReduceOp.MIN)
+            parity = dict(parity, max_rel_all_ranks=worst, argmax_equal_all_ranks=bool(t2.item() > 0.5), ranks=world)
 
-    # ---- end to end through the C ABI with HOST buffers (pinned): H2D of x, track + refine, D2H of results
+    # ---- end to end through the C ABI with HOST buffers (pinned): H2D of x + target sizes, the same frame, D2H
     lib = _lib.load()
-    A = 5
     xh = [torch.empty(B, 3, S, S).pin_memory() for _ in range(2)]
-    for t in xh:
-        t.copy_(xs[0].cpu())
-    clsh = [torch.empty(B, 2 * A, R, R).pin_memory() for _ in range(2)]
-    loch = [torch.empty(B, 4 * A, R, R).pin_memory() for _ in range(2)]
-    maskh = [torch.empty(B, 127 * 127).pin_memory() for _ in range(2)]
-    posh = pos.cpu().contiguous().pin_memory()
+    for t_ in xh:
+        t_.copy_(xs[0].cpu())
+    tszh = tsz_dev.cpu().contiguous().pin_memory()
+    rech = [torch.empty(B, 8).pin_memory() for _ in range(2)]
+    refh = [torch.empty(B, 127 * 127).pin_memory() for _ in range(2)] if sharp else [None, None]
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    ios = {}
 
-    def submit(i):
+    def make_io(g, mask_head):
+        io = _lib.SmStepIO()
+        io.x_host = xh[g].data_ptr(); io.tsz_host = tszh.data_ptr()
+        io.anchors_dev = anchors_dev.data_ptr(); io.window_dev = window_dev.data_ptr()
+        io.penalty_k = PENALTY_K; io.window_influence = WINDOW_INFLUENCE
+        io.flags = ((_lib.SM_TRACK_MASK_FEATURES if sharp else 0) |
+                    (_lib.SM_TRACK_MASK_HEAD if (sharp and mask_head) else 0))
+        io.records_host = rech[g].data_ptr()
+        io.refine_host = refh[g].data_ptr() if sharp else None
+        return io
+
+    def submit(g, mask_head):
+        io = ios.setdefault((g, mask_head), make_io(g, mask_head))
         tk = C.c_int32()
-        _lib.check(lib.sm_track_host_async(m.handle, 0, B, xh[i % 2].data_ptr(), clsh[i % 2].data_ptr(),
-                                           loch[i % 2].data_ptr(), posh.data_ptr(), maskh[i % 2].data_ptr(), stream,
-                                           C.byref(tk)))
+        _lib.check(lib.sm_step_host_async(m.handle, g * B, B, C.byref(io), stream, C.byref(tk)))
         return tk.value
 
-    def host_loop(n):
-        # a user with a stream of frames keeps one step in flight: submit frame k+1, then collect frame k
-        prev = None
+    def host_loop(n, mask_head, groups=2):
+        # two independent groups of B tracker streams alternate: while group 0's frame is on the GPU the host
+        # collects group 1's results and submits its next frame (a group's frame k+1 is only submitted after its
+        # frame k has been waited for — the dependency a real tracker has).  groups=1: strictly serial.
+        pending = [None, None]
         for i in range(n):
-            tk = submit(i)
-            if prev is not None:
-                _lib.check(lib.sm_track_host_wait(m.handle, prev))
-            prev = tk
-        _lib.check(lib.sm_track_host_wait(m.handle, prev))
-    host_loop(3)
-    barrier()
-    t0 = time.perf_counter()
-    host_loop(args.steps)      # every step's results are in host memory when this returns
-    dt = max_over_ranks(time.perf_counter() - t0, device=dev)
-    e2e_fps = world * B * args.steps / dt
-    h2d = xh[0].numel() * 4 + posh.numel() * 4
-    d2h = (clsh[0].numel() + loch[0].numel() + maskh[0].numel()) * 4
+            g = i % groups
+            if pending[g] is not None:
+                _lib.check(lib.sm_track_host_wait(m.handle, pending[g]))
+            pending[g] = submit(g, mask_head)
+        for g in range(groups):
+            if pending[g] is not None:
+                _lib.check(lib.sm_track_host_wait(m.handle, pending[g]))
+
+    def e2e_rate(mask_head, groups, n):
+        host_loop(3, mask_head, groups)
+        barrier()
+        t0 = time.perf_counter()
+        host_loop(n, mask_head, groups)      # every step's results are in host memory when this returns
+        dt = max_over_ranks(time.perf_counter() - t0, device=dev)
+        return world * B * n / dt, dt
+    n_e2e = max(args.steps, math.ceil(args.min_seconds * 1e3 / est_ms))
+    e2e_fps, e2e_dt = e2e_rate(True, 2, n_e2e)
+    e2e_skip = e2e_rate(False, 2, max(3, n_e2e // 4))[0] if sharp else None
+    e2e_serial = e2e_rate(True, 1, max(3, n_e2e // 4))[0]
+    h2d = xh[0].numel() * 4 + tszh.numel() * 8
+    d2h = rech[0].numel() * 4 + (refh[0].numel() * 4 if sharp else 0)
 
     if rank != 0:
         if world > 1:
@@ -356,11 +482,12 @@ def run_gpu(args, rank, local_rank, world):
                 f.write(f"{name}\t{cat}\t{t:.4f}\t{fl / 1e9:.2f}\t{by / 1e6:.1f}\t{fl / (t * 1e-3) / 1e12:.1f}\t"
                         f"{by / (t * 1e-3) / 1e9:.0f}\n")
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath) and args.precision == "exact" and B == 64 and S == 255:
+    tpath = os.path.join(ROOT, "profiles", args.traffic_file)
+    if os.path.exists(tpath) and args.precision == "exact" and B == 64 and S == 255 and sharp:
         tj = json.load(open(tpath))           # ncu dram__bytes_read+write of the family's launches in one step
         traffic = {"bytes_per_step": tj["conv_gemm_traffic_bytes_per_step"],
-                   "launches_per_step": tj["conv_gemm_launches_per_step"], "source": "profiles/r01_traffic.json (ncu)"}
+                   "launches_per_step": tj["conv_gemm_launches_per_step"], "measured_in_run": False,
+                   "source": f"profiles/{args.traffic_file} (committed ncu capture of this command, not measured in this run)"}
     roofline = {
         "bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv family, all layers of one step)",
         "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
@@ -371,7 +498,7 @@ def run_gpu(args, rank, local_rank, world):
         "launches_per_step": gemm["launches"], "ms_per_step": gemm["ms"], "share_of_step": gemm["ms"] / tot_ms,
         "algorithmic_gflop_per_step": gemm["flops"] / 1e9,
         "note": "algorithmic FLOPs (2*M*N*K per conv, no padding, no x3 for the split-fp16 passes) / summed "
-                "CUDA-event durations of the launches",
+                "CUDA-event durations of the launches (one launch per layer over the whole batch, lanes off)",
         "top_layers": [{"layer": k, "ms": v[0], "tflops": v[1] / (v[0] * 1e-3) / 1e12} for k, v in top],
     }
     by_cat = {k: {"ms": round(v["ms"], 4), "launches": round(v["launches"], 1),
@@ -379,15 +506,16 @@ def run_gpu(args, rank, local_rank, world):
                   "gbps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else 0.0}
               for k, v in sorted(cats.items(), key=lambda kv: -kv[1]["ms"])}
 
-    # ---- standalone depthwise xcorr operator (the "xcorr GB/s" half of the metric): 3 branches x 64 streams
-    planes_b = 3 * B
+    # ---- standalone depthwise xcorr operator (the "xcorr GB/s" half of the metric): branches x streams planes
+    nbr = 3 if sharp else 2
+    planes_b = nbr * B
     xc = torch.randn(planes_b, 256, R + 4, R + 4, device=dev)
     kc = torch.randn(planes_b, 256, 5, 5, device=dev)
     for _ in range(3):
         smb.conv2d_dw_group(xc, kc)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
-    reps = 10
+    reps = 20
     e0.record()
     for _ in range(reps):
         out = smb.conv2d_dw_group(xc, kc)
@@ -398,53 +526,136 @@ def run_gpu(args, rank, local_rank, world):
     xgbs = xbytes / (xms * 1e-3) / 1e9
     del xc, kc, out
 
+    gfl = (GFLOP_SHARP if sharp else GFLOP_RPN).get(S, 0.0)
     result = {
-        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "metric": metric_name(args), "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warm, "ms_per_step": ms / n_pass, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None,
         "dtype": "f16x3 (hi+lo split fp16 operands on tcgen05, f32 accumulate; f32 CUDA-core stem/xcorr/refine)"
                  if args.precision == "exact" else "f16 (single-pass tcgen05, f32 accumulate)",
         "data": "synthetic", "config": workload_config(args, B, world),
         "precision_mode": args.precision,
-        "algorithmic_tflops": fps * GFLOP_PER_FRAME.get(S, 0.0) / 1e3,
+        "passes_per_step": passes, "timed_region_s": ms * 1e-3,
+        "timing_note": f"the timed region covers steps x passes_per_step = {n_pass} passes over a batch "
+                       f"(>= {args.min_seconds} s); ms_per_step and value are per pass",
+        "algorithmic_tflops": fps * gfl / 1e3,
         "value_skip_dead_mask_head": fps_skip,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "sm_track_host_async / sm_track_host_wait (C ABI, pinned host buffers, one step in flight; "
-                       "refine positions supplied by the host; mask head skipped as under --refine)"},
+                "timed_region_s": e2e_dt, "value_skip_dead_mask_head": e2e_skip, "value_serial_one_group": e2e_serial,
+                "api": "sm_step_host_async / sm_track_host_wait (C ABI, pinned host buffers): H2D frames + target "
+                       "sizes -> track_mask incl. mask head -> on-device selection -> refine at the selected position "
+                       "-> D2H records + refine logits; same flags as `value`; two independent groups of "
+                       "batch_per_gpu streams alternate (one step in flight), value_serial_one_group = no overlap"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
         "kernels_ms_per_step": by_cat,
         "xcorr": {"op": "sm_xcorr_depthwise fp32 NCHW", "planes": planes_b * 256, "ms": xms, "GBps": xgbs,
                   "peak": peaks["hbm_gbs"], "frac": xgbs / peaks["hbm_gbs"], "peak_source": peaks["src"]},
+        "parity_check": parity,
         "device_bytes": m.device_bytes,
     }
     if world == 1 and not args.no_cpu:
-        result["cpu_baseline"] = cpu_baseline(args)
+        cfps, cores, sample, _ = run_cpu_fleet(args, seconds=args.cpu_seconds)
+        result["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores, "host_cpus": os.cpu_count(),
+                                  "kind": "port", "sample": sample}
+    if world == 1 and not args.no_context:
+        del m
+        torch.cuda.empty_cache()
+        result["context"] = {"cudnn": cudnn_context(args, dev)}
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
 
 
+def verify_against_oracle(args, m, sd, z, x, anchors_dev, window_dev, tsz_dev, B, dev, sharp):
+    """Outputs of one engine step at THIS run's batch / tile / lane configuration vs the CPU oracle, for the first
+    and the last stream of this rank (max|a-b| / max|b| per tensor, the parity metric of tests/conftest.py)."""
+    import torch
+    from oracle.siammask_oracle import Oracle
+    out = m.step(x, anchors_dev, window_dev, tsz_dev, PENALTY_K, WINDOW_INFLUENCE, refine=sharp, mask_head=sharp,
+                 mask_col=sharp)
+    torch.cuda.synchronize(dev)
+    streams = sorted({0, B - 1})
+    o = Oracle(sd)
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    errs, same = {}, True
+
+    def rel(a, b):
+        a, b = a.detach().double().cpu(), b.detach().double().cpu()
+        return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    for b in streams:
+        o.template(z[b:b + 1].cpu())
+        if sharp:
+            ocls, oloc, omask = o.track_mask(x[b:b + 1].cpu())
+        else:
+            ocls, oloc = o.track(x[b:b + 1].cpu())
+        errs["cls"] = max(errs.get("cls", 0.0), rel(out["cls"][b:b + 1], ocls))
+        errs["loc"] = max(errs.get("loc", 0.0), rel(out["loc"][b:b + 1], oloc))
+        # the selection of the engine vs the reference arithmetic (numpy, float64) on the ORACLE's cls/loc
+        from oracle.ref_loop import select_numpy
+        from siammask_b200 import anchors as anc
+        R = (args.search - 127) // 8 + 9
+        bid, box, score, pen, ps = select_numpy(ocls, oloc, anc.generate_anchor({"stride": 8, "ratios": [0.33, 0.5, 1, 2, 3],
+                                                                                   "scales": [8], "round_dight": 0}, R),
+                                                anc.cosine_window(R, 5), tsz_dev[b].cpu().numpy(), PENALTY_K,
+                                                WINDOW_INFLUENCE)
+        same = same and int(out["best"][b]) == bid
+        if sharp:
+            pos = tuple(int(v) for v in out["pos"][b].cpu())
+            errs["refine"] = max(errs.get("refine", 0.0), rel(out["refine"][b:b + 1], o.track_refine(pos)))
+            errs["mask_col"] = max(errs.get("mask_col", 0.0), rel(out["mask_col"][b], omask[0, :, pos[0], pos[1]]))
+    return {"max_rel": max(errs.values()), "per_tensor": errs, "argmax_equal": same, "streams": streams,
+            "tolerance": 1e-3, "ok": max(errs.values()) <= 1e-3, "oracle": "oracle/siammask_oracle.py (torch CPU fp32)"}
+
+
+PRESETS = {2: dict(batch=64, search=255, rpn_only=False),     # BASELINE.json configs[1] (and configs[3] at N=8)
+           3: dict(batch=256, search=255, rpn_only=True),     # configs[2]
+           4: dict(batch=64, search=255, rpn_only=False),     # configs[3]: 512 streams over 8 GPUs = 64 per GPU
+           5: dict(batch=128, search=383, rpn_only=False)}    # configs[4]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="paired tracker streams per GPU")
-    ap.add_argument("--search", type=int, default=255)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "_cpu_worker"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(PRESETS),
+                    help="BASELINE.json config number (1-based): 2 = B=64 sharp (default), 3 = SiamRPN-only B=256, "
+                         "4 = 512 streams on 8 GPUs, 5 = search 383 B=128")
+    ap.add_argument("--batch", type=int, default=None, help="paired tracker streams per GPU (overrides the preset)")
+    ap.add_argument("--search", type=int, default=None)
     ap.add_argument("--precision", default="exact", choices=["exact", "fast"])
-    ap.add_argument("--rpn-only", action="store_true",
-                    help="SiamRPN-only engine (experiments/siamrpn_resnet): step = track -> cls/loc (BASELINE configs[2])")
-    ap.add_argument("--ref-batch", type=int, default=2, help="frames per step of the CPU reference arm")
+    ap.add_argument("--rpn-only", action="store_true", default=None,
+                    help="SiamRPN-only engine (experiments/siamrpn_resnet): step = track -> cls/loc")
+    ap.add_argument("--min-seconds", type=float, default=2.0, help="minimum length of every timed region")
+    ap.add_argument("--ref-batch", type=int, default=2, help="frames per step of each CPU reference worker")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="torch threads per CPU worker (0 = pick)")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="length of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-context", action="store_true", help="skip the PyTorch/cuDNN context leg")
+    ap.add_argument("--no-verify", dest="verify", action="store_false", help="skip the oracle parity check")
+    ap.add_argument("--traffic-file", default="r02_traffic.json")
     ap.add_argument("--dump-layers", default=None, help="write the per-launch CUDA-event table of one step here")
+    # internal (cpu worker processes)
+    ap.add_argument("--threads", type=int, default=8)
+    ap.add_argument("--worker-id", type=int, default=0)
+    ap.add_argument("--worker-seconds", type=float, default=0.0)
     args = ap.parse_args()
+    preset = PRESETS[args.config]
+    if args.batch is None:
+        args.batch = preset["batch"]
+    if args.search is None:
+        args.search = preset["search"]
+    if args.rpn_only is None:
+        args.rpn_only = preset["rpn_only"]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
+    if args.impl == "_cpu_worker":
+        _cpu_worker(args)
+    elif args.impl == "reference":
         run_reference(args, rank)
     else:
         run_gpu(args, rank, local_rank, world)

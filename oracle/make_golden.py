@@ -76,8 +76,28 @@ def tracker_loop_golden(sd):
     np.savez_compressed(os.path.join(OUT, "tracker_loop.npz"), **{k: np.asarray(v) for k, v in rec.items()})
 
 
+def sharp_383_golden(m):
+    """Sharp path at search 383 (BASELINE.json configs[4]): 41x41 response, refine at the corners and an interior
+    position, 21 mask-head channels, sub-sampled pyramid — from the unmodified reference model."""
+    from oracle.calibrate import synthetic_inputs
+    z, x = synthetic_inputs(3, 1, search=383)
+    m.template(z)
+    cls, loc, mask = m.track_mask(x)
+    feats = {f"p{i}": sub(f, 509) for i, f in enumerate(m.feature)}
+    ref = {f"refine_{dy}_{dx}": m.track_refine((dy, dx)).numpy() for dy, dx in ((0, 0), (40, 40), (7, 33))}
+    np.savez_compressed(os.path.join(OUT, "sharp_b1_s383.npz"), cls=cls.numpy(), loc=loc.numpy(),
+                        mask_sub=mask[:, slice(0, 3969, 193)].numpy(), search=sub(m.search, 13),
+                        corr=sub(m.corr_feature, 13), **feats, **ref)
+
+
 def main():
     from oracle.calibrate import calibrated_state_dict, synthetic_inputs
+    if "--only-383" in sys.argv:          # add the sharp@383 vectors without rewriting the other files
+        warnings.filterwarnings("ignore")
+        torch.set_num_threads(8)
+        with torch.no_grad():
+            sharp_383_golden(reference_model(calibrated_state_dict(0)))
+        return
     warnings.filterwarnings("ignore")
     torch.set_num_threads(8)
     sd = calibrated_state_dict(0)
@@ -104,6 +124,7 @@ def main():
         m.template(z3)
         cls3, loc3 = m.track(x3)
         np.savez_compressed(os.path.join(OUT, "rpn_b1_s383.npz"), cls=cls3.numpy(), loc=loc3.numpy())
+        sharp_383_golden(m)
         # --- standalone depthwise xcorr (models/rpn.py:32-38)
         sys.path[:0] = [REF]
         from models.rpn import conv2d_dw_group

@@ -127,6 +127,8 @@ void launch_xcorr_nhwc(const Act& x, const __half* k_hi, const __half* k_lo, int
                        cudaStream_t st);
 void launch_xcorr_nchw_f32(const float* x, const float* k, float* out, int planes, int H, int W, int kh, int kw,
                            cudaStream_t st);
+int launch_xcorr_bulk_f32(const float* x, const float* k, float* out, int planes, int H, int W, int kh, int kw,
+                          cudaStream_t st);
 void launch_crop_center(const Act& in, int crop, Act out, cudaStream_t st);
 void launch_refine_crop(const Act& in, const int32_t* pos, int pos_max, int scale, int padv, int size, Act out,
                         cudaStream_t st);

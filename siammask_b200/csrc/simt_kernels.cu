@@ -5,6 +5,7 @@
 #include "common.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace smk {
@@ -856,6 +857,14 @@ void launch_xcorr_nhwc(const Act& x, const __half* k_hi, const __half* k_lo, int
 void launch_xcorr_nchw_f32(const float* x, const float* k, float* out, int planes, int H, int W, int kh, int kw,
                            cudaStream_t st) {
   SMK_CHECK(H >= kh && W >= kw && planes > 0, "xcorr shapes");
+  // bulk-copy pipeline (xcorr_bulk_sm100.cu) for whole tiles of planes; the one-warp-per-plane kernel takes the rest
+  static const bool no_bulk = getenv("SMB200_XCORR_NO_BULK") != nullptr;
+  const int done = no_bulk ? 0 : launch_xcorr_bulk_f32(x, k, out, planes, H, W, kh, kw, st);
+  if (done >= planes) return;
+  x += (size_t)done * H * W;
+  k += (size_t)done * kh * kw;
+  out += (size_t)done * (H - kh + 1) * (W - kw + 1);
+  planes -= done;
   if (kh == 5 && kw == 5) {
     const int warps = 8;
     // whole plane in flight when it has at most 32 rows (29 @255), two batches of 24 otherwise (45 @383)

@@ -116,8 +116,10 @@ def test_conv_small_channels_simt_only():
         smb.conv2d(x, w, None, None, 1, 1, 1, backend="tensor")
 
 
-@pytest.mark.parametrize("shape", [(2, 8, 29, 29, 5), (1, 256, 29, 29, 5), (3, 16, 45, 45, 5), (2, 4, 12, 12, 3),
-                                   (1, 3, 7, 7, 7)], ids=str)
+# 256 / 150 planes @29: 8 resp. 4 whole tiles of the bulk-copy pipeline (+ a 22-plane remainder on the one-warp-per-plane
+# kernel); 48 / 35 planes @45: 6 resp. 4 tiles of 8 (+3); the small ones never reach the bulk path
+@pytest.mark.parametrize("shape", [(2, 8, 29, 29, 5), (1, 256, 29, 29, 5), (3, 50, 29, 29, 5), (3, 16, 45, 45, 5),
+                                   (1, 35, 45, 45, 5), (2, 4, 12, 12, 3), (1, 3, 7, 7, 7)], ids=str)
 def test_xcorr_depthwise_matches_oracle(shape):
     B, Cn, H, W, k = shape
     g = torch.Generator().manual_seed(5)
@@ -127,6 +129,17 @@ def test_xcorr_depthwise_matches_oracle(shape):
     assert_close(out, Oracle.xcorr_depthwise(x, ker), 2e-6, f"xcorr {shape}")
     loops = torch.from_numpy(xcorr_depthwise_loops(x.numpy(), ker.numpy())).float()
     assert_close(out, loops, 2e-6, f"xcorr {shape} vs loops")
+
+
+def test_xcorr_misaligned_view_takes_the_fallback():
+    """cp.async.bulk needs 16-byte aligned operands: a view that starts one 3364-byte plane into its storage is only
+    4-byte aligned and must still give the right answer (one-warp-per-plane kernel)."""
+    g = torch.Generator().manual_seed(6)
+    xb = torch.randn(65, 1, 29, 29, generator=g).cuda()
+    kb = torch.randn(65, 1, 5, 5, generator=g).cuda()
+    x, ker = xb[1:], kb[1:]
+    assert x.data_ptr() % 16 != 0 and x.is_contiguous()
+    assert_close(smb.conv2d_dw_group(x, ker), Oracle.xcorr_depthwise(x.cpu(), ker.cpu()), 2e-6, "xcorr misaligned view")
 
 
 def test_xcorr_golden_and_properties():

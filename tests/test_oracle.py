@@ -78,6 +78,23 @@ def test_oracle_matches_golden_batched_and_383(calib_sd):
     assert_close(loc, g["loc"], GOLDEN_TOL, "loc @383")
 
 
+def test_oracle_matches_golden_sharp_383(calib_sd):
+    """Sharp path at search 383 (BASELINE.json configs[4]): mask branch + refine incl. the corner positions."""
+    g = _g("sharp_b1_s383.npz")
+    z, x = synthetic_inputs(3, 1, search=383)
+    o = Oracle(calib_sd)
+    o.template(z)
+    cls, loc, mask = o.track_mask(x)
+    assert mask.shape == (1, 3969, 41, 41)
+    assert_close(cls, g["cls"], GOLDEN_TOL, "cls @383")
+    assert_close(mask[:, slice(0, 3969, 193)], g["mask_sub"], GOLDEN_TOL, "mask head @383")
+    for i in range(4):
+        assert_close(o.feature[i].flatten()[::509], g[f"p{i}"], GOLDEN_TOL, f"p{i} @383")
+    assert_close(o.corr_feature.flatten()[::13], g["corr"], GOLDEN_TOL, "corr @383")
+    for pos in ((0, 0), (40, 40), (7, 33)):
+        assert_close(o.track_refine(pos), g[f"refine_{pos[0]}_{pos[1]}"], GOLDEN_TOL, f"refine {pos} @383")
+
+
 def test_per_stream_refine_equals_per_sample_loop(calib_sd):
     z, x = synthetic_inputs(4, 2)
     o = Oracle(calib_sd)
