@@ -107,6 +107,25 @@ int sm_select(sm_engine* e, int32_t B, const float* cls, const float* loc, const
               const double* target_sz_in_crop, double penalty_k, double window_influence, int32_t* best_idx, int32_t* pos,
               float* records, void* stream);
 
+/* Device-resident tracker state for B concurrent streams — the host arithmetic of siamese_track around the network
+ * (tools/test.py:172-200, 239-249, 263-282, 305-315), float64 as numpy evaluates it, so that frame k+1's crop follows
+ * from frame k's result without a host round trip.  state f64 [B][4] = target_pos (x, y), target_sz (w, h), device.
+ *  sm_tracker_prepare: search window of the next frame -> boxes int32 [B][8] for sm_crop_resize (:180-198, :71-76),
+ *    target_sz_in_crop f64 [B][2] for sm_select / sm_step (:226), aux f64 [B][4] = scale_x, round(s_x), crop_box x0, y0.
+ *  sm_tracker_update: records f32 [B][8] of sm_select / sm_step + aux -> lr-smoothed, frame-clamped state (:239-249,
+ *    :305-315; the penalty of the winner is re-evaluated in float64); maps f64 [B][6] (may be NULL) = forward affine map
+ *    of crop_back (:263-275) for sm_warp_affine; out f64 [B][8] (may be NULL) = x, y, w, h, score, penalty, lr, best index.
+ *    im_wh int32 [B][2] = frame width, height. */
+typedef struct sm_tracker_hp {
+  double context_amount, penalty_k, window_influence, lr;   /* utils/tracker_config.py:10-21 / config_davis.json */
+  int32_t exemplar_size, instance_size, total_stride, base_size, out_size, reserved;
+} sm_tracker_hp;
+int sm_tracker_prepare(int32_t B, const double* state, const int32_t* avg_chans, const sm_tracker_hp* hp, int32_t* boxes,
+                       double* target_sz_in_crop, double* aux, void* stream);
+int sm_tracker_update(int32_t B, double* state, const float* records, const double* aux, const int32_t* im_wh,
+                      const sm_tracker_hp* hp, int32_t anchor_num, int32_t score_size, double* maps, double* out,
+                      void* stream);
+
 /* One whole frame of siamese_track (tools/test.py:201-261) on the device, all pointers device pointers:
  * sm_track(flags) -> sm_select -> sm_refine at the position sm_select chose (refine_out != NULL needs
  * SM_TRACK_MASK_FEATURES) -> optionally mask_col f32 [B][3969] = mask[b, :, dy, dx] (:259-260; needs

@@ -32,6 +32,12 @@ class SmStepIO(C.Structure):
                 ("mask_col_host", C.c_void_p), ("cls_host", C.c_void_p), ("loc_host", C.c_void_p)]
 
 
+class SmTrackerHp(C.Structure):
+    _fields_ = [("context_amount", C.c_double), ("penalty_k", C.c_double), ("window_influence", C.c_double),
+                ("lr", C.c_double), ("exemplar_size", C.c_int32), ("instance_size", C.c_int32),
+                ("total_stride", C.c_int32), ("base_size", C.c_int32), ("out_size", C.c_int32), ("reserved", C.c_int32)]
+
+
 # name -> (restype, argtypes); mirrors include/siammask_b200.h one to one
 SIGNATURES = {
     "sm_engine_create": (C.c_int, [C.POINTER(SmConfig), C.POINTER(C.c_void_p)]),
@@ -53,6 +59,10 @@ SIGNATURES = {
     "sm_warp_affine": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                  C.c_float, C.c_int32, C.c_void_p]),
     "sm_select": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 5 + [C.c_double, C.c_double] + [C.c_void_p] * 4),
+    "sm_tracker_prepare": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(SmTrackerHp), C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
+    "sm_tracker_update": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SmTrackerHp),
+                                    C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sm_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 4 + [C.c_double, C.c_double, C.c_int32] +
                 [C.c_void_p] * 9),
     "sm_step_host_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(SmStepIO), C.c_void_p,

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsiammask_b200.so")
-SOURCES = ["conv_gemm_sm100.cu", "stem_sm100.cu", "simt_kernels.cu", "xcorr_bulk_sm100.cu", "engine.cu"]
+SOURCES = ["conv_gemm_sm100.cu", "conv3x3_patch_sm100.cu", "stem_sm100.cu", "simt_kernels.cu", "xcorr_bulk_sm100.cu", "engine.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", os.path.join("..", "..", "include", "siammask_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

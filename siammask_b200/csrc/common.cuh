@@ -72,6 +72,12 @@ struct GemmInput {
   int w_col0;
 };
 
+// hyper-parameters of the tracker loop (utils/tracker_config.py + config_davis.json), mirrors sm_tracker_hp
+struct TrackerHp {
+  double context_amount, penalty_k, window_influence, lr;
+  int32_t exemplar_size, instance_size, total_stride, base_size, out_size, reserved;
+};
+
 struct CudaError : std::runtime_error {
   using std::runtime_error::runtime_error;
 };
@@ -113,6 +119,15 @@ void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, i
                        const __half* w_lo, int cout_pad, int w_ld, const Epilogue& ep, int nsplit, int num_sms,
                        cudaStream_t st, bool reverse_m = false);
 
+CUtensorMap make_map_tiled_nd(const __half* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                              const uint32_t* box, int swizzle_bytes);
+
+// conv3x3_patch_sm100.cu : 3x3 / s1 / p1 / Cin == Cout in {64, 128} on a resident input patch (no im2col traffic)
+int patch_conv_mode();
+bool patch_conv_supported(const Act& in, const ConvGeom& g);
+void launch_conv3x3_patch(const Act& in, const ConvGeom& g, const __half* w_hi, const __half* w_lo, int w_ld,
+                          const Epilogue& ep, int nsplit, int num_sms, cudaStream_t st);
+
 // stem_sm100.cu : 7x7/2 stem on the tensor cores (weights [64][192] K-major, k = (r*7+s)*3+c, pow2-scaled)
 void launch_stem_tc(const float* x_nchw, int B, int S, const __half* w_hi, const __half* w_lo, const float* alpha,
                     const float* beta, Act out, int num_sms, cudaStream_t st);
@@ -140,6 +155,10 @@ void launch_split_to_f32(const Act& in, float* out, cudaStream_t st);
 void launch_import_nchw(const float* x_nchw, Act out, cudaStream_t st);
 void launch_warp_affine(const float* src, int sh, int sw, const double* maps, float* dst, int dh, int dw, float border,
                         int B, cudaStream_t st);
+void launch_tracker_prepare(int B, const double* state, const int32_t* avg, const TrackerHp& hp, int32_t* boxes,
+                            double* tsz, double* aux, cudaStream_t st);
+void launch_tracker_update(int B, double* state, const float* rec, const double* aux, const int32_t* imsize,
+                           const TrackerHp& hp, int A, int R, double* maps, double* out, cudaStream_t st);
 void launch_crop_resize(const uint8_t* frames, size_t frame_stride, int H, int W, const int32_t* box, int B, int model,
                         float* out, cudaStream_t st);
 void launch_select(const float* cls, const float* loc, const float* anchors, const float* window, const double* tsz,

@@ -36,7 +36,9 @@
 #include "ptx.cuh"
 
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
+#include <unordered_map>
 
 namespace smk {
 
@@ -546,7 +548,40 @@ const DriverApi& driver_api() {
   return api;
 }
 
-CUtensorMap make_map_2d(const __half* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
+// Tensor-map cache.  cuTensorMapEncode* costs a few microseconds on the host and a launch needs up to eight maps; the
+// engine's bump arenas hand out the same addresses every step, so the (pointer, geometry) key of every map repeats from
+// the second step on.  Keyed by the encode arguments themselves, so a hit is exactly what the driver would build.
+struct MapKey {
+  uint64_t v[16];
+  bool operator==(const MapKey& o) const { return std::memcmp(v, o.v, sizeof v) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (uint64_t x : k.v) { h ^= x + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); }
+    return (size_t)h;
+  }
+};
+template <typename F>
+CUtensorMap cached_map(const MapKey& key, F&& encode) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static const bool off = getenv("SMB200_NO_MAP_CACHE") != nullptr;
+  if (off) return encode();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  MapKey k = key;
+  k.v[15] = (uint64_t)dev;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(k);
+  if (it != cache.end()) return it->second;
+  if (cache.size() > 65536) cache.clear();             // unbounded callers (standalone ops on fresh buffers)
+  CUtensorMap m = encode();
+  cache.emplace(k, m);
+  return m;
+}
+
+CUtensorMap make_map_2d_raw(const __half* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
   CUtensorMap m;
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {inner * sizeof(__half)};
@@ -561,7 +596,13 @@ CUtensorMap make_map_2d(const __half* base, uint64_t inner, uint64_t outer, uint
   return m;
 }
 
-CUtensorMap make_map_epilogue(const __half* base, uint64_t cout, uint64_t m) {
+CUtensorMap make_map_2d(const __half* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
+  MapKey k{};
+  k.v[0] = 1; k.v[1] = (uint64_t)base; k.v[2] = inner; k.v[3] = outer; k.v[4] = box_inner; k.v[5] = box_outer;
+  return cached_map(k, [&] { return make_map_2d_raw(base, inner, outer, box_inner, box_outer); });
+}
+
+CUtensorMap make_map_epilogue_raw(const __half* base, uint64_t cout, uint64_t m) {
   CUtensorMap t;
   cuuint64_t dims[2] = {cout, m};
   cuuint64_t strides[1] = {cout * sizeof(__half)};
@@ -574,7 +615,13 @@ CUtensorMap make_map_epilogue(const __half* base, uint64_t cout, uint64_t m) {
   return t;
 }
 
-CUtensorMap make_map_im2col(const __half* base, const Act& in, const ConvGeom& g, int bk) {
+CUtensorMap make_map_epilogue(const __half* base, uint64_t cout, uint64_t m) {
+  MapKey k{};
+  k.v[0] = 2; k.v[1] = (uint64_t)base; k.v[2] = cout; k.v[3] = m;
+  return cached_map(k, [&] { return make_map_epilogue_raw(base, cout, m); });
+}
+
+CUtensorMap make_map_im2col_raw(const __half* base, const Act& in, const ConvGeom& g, int bk) {
   CUtensorMap m;
   cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.B};
   cuuint64_t strides[3] = {(cuuint64_t)in.C * 2, (cuuint64_t)in.W * in.C * 2, (cuuint64_t)in.H * in.W * in.C * 2};
@@ -594,6 +641,15 @@ CUtensorMap make_map_im2col(const __half* base, const Act& in, const ConvGeom& g
   if (api.driver_version <= 13010 && in.numel() * sizeof(__half) < 131072)
     reinterpret_cast<uint64_t*>(&m)[1] &= ~(1ull << 21);
   return m;
+}
+
+CUtensorMap make_map_im2col(const __half* base, const Act& in, const ConvGeom& g, int bk) {
+  MapKey k{};
+  k.v[0] = 3; k.v[1] = (uint64_t)base;
+  k.v[2] = ((uint64_t)in.B << 32) | (uint32_t)in.H; k.v[3] = ((uint64_t)in.W << 32) | (uint32_t)in.C;
+  k.v[4] = ((uint64_t)g.KH << 32) | (uint32_t)g.KW; k.v[5] = ((uint64_t)g.stride << 32) | (uint32_t)g.pad;
+  k.v[6] = ((uint64_t)g.dil << 32) | (uint32_t)bk;
+  return cached_map(k, [&] { return make_map_im2col_raw(base, in, g, bk); });
 }
 
 template <int BLOCK_N, int NSPLIT, int BK = 64, int CG = 1>
@@ -628,7 +684,7 @@ void launch_cfg(const GemmParams& p, int num_sms, cudaStream_t st) {
 }  // namespace
 
 // 2-D fp16 tensor map with a chosen swizzle span (32 / 64 / 128 bytes); shared with stem_sm100.cu
-CUtensorMap make_map_2d_any(const __half* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer,
+static CUtensorMap make_map_2d_any_raw(const __half* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer,
                             int swizzle_bytes) {
   CUtensorMap m;
   cuuint64_t dims[2] = {inner, outer};
@@ -642,6 +698,45 @@ CUtensorMap make_map_2d_any(const __half* base, uint64_t inner, uint64_t outer, 
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SMK_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed, code " + std::to_string((int)r));
   return m;
+}
+
+CUtensorMap make_map_2d_any(const __half* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer,
+                            int swizzle_bytes) {
+  MapKey k{};
+  k.v[0] = 5; k.v[1] = (uint64_t)base; k.v[2] = inner; k.v[3] = outer; k.v[4] = box_inner; k.v[5] = box_outer;
+  k.v[6] = (uint64_t)swizzle_bytes;
+  return cached_map(k, [&] { return make_map_2d_any_raw(base, inner, outer, box_inner, box_outer, swizzle_bytes); });
+}
+
+// N-dimensional tiled-mode fp16 tensor map (rank 2..5), operand-load flavour (L2 promotion 256 B); shared with
+// conv3x3_patch_sm100.cu
+static CUtensorMap make_map_tiled_nd_raw(const __half* base, int rank, const uint64_t* dims,
+                                         const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+  SMK_CHECK(rank >= 2 && rank <= 5, "tensor map rank");
+  CUtensorMap m;
+  cuuint64_t d[5], sb[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) sb[i] = strides_bytes[i];
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = driver_api().tiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<__half*>(base), d, sb,
+                                  bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SMK_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (nd) failed, code " + std::to_string((int)r));
+  return m;
+}
+
+CUtensorMap make_map_tiled_nd(const __half* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                              const uint32_t* box, int swizzle_bytes) {
+  SMK_CHECK(rank >= 2 && rank <= 5, "tensor map rank");
+  MapKey k{};
+  k.v[0] = 4 | ((uint64_t)rank << 8) | ((uint64_t)swizzle_bytes << 16);
+  k.v[1] = (uint64_t)base;
+  for (int i = 0; i < rank; ++i) k.v[2 + i] = dims[i] | ((uint64_t)box[i] << 40);
+  for (int i = 0; i + 1 < rank; ++i) k.v[7 + i] = strides_bytes[i];
+  return cached_map(k, [&] { return make_map_tiled_nd_raw(base, rank, dims, strides_bytes, box, swizzle_bytes); });
 }
 
 bool gemm_conv_supported(const ConvGeom& g) { return g.Cin % CIN_GRAIN == 0 && g.Cout >= 1; }

@@ -830,7 +830,10 @@ void Engine::conv_into(const Act& in, const ConvW& Lw, Epilogue ep, cudaStream_t
     if (in2 != nullptr && in2->numel() > big->numel()) big = in2;
     if (res != nullptr && res->numel() > big->numel()) big = res;
     static const bool no_reverse = std::getenv("SMB200_NO_REVERSE") != nullptr;   // A/B switch for measurements
-    const bool reverse = !no_reverse && end_of(*big) > 0;
+    // bottleneck conv2 (3x3 / s1 / p1, 64 or 128 channels): resident-patch kernel, walks its tiles front to back
+    const bool use_patch = patch_conv_mode() != 0 && in2 == nullptr && res == nullptr &&
+                           ep.out_mode == OUT_NHWC_SPLIT && patch_conv_supported(in, Lw.g);
+    const bool reverse = !use_patch && !no_reverse && end_of(*big) > 0;
     const int now_end = reverse ? -1 : +1;
     last_end_[in.hi] = now_end;
     if (in2 != nullptr) last_end_[in2->hi] = now_end;
@@ -847,8 +850,11 @@ void Engine::conv_into(const Act& in, const ConvW& Lw, Epilogue ep, cudaStream_t
       if (Lw.has_diag) ident = res;                                  // residual through the MMA pipeline
       else { ep.res_hi = res->hi; ep.res_lo = res->lo; }             // epilogue-side add
     }
-    launch_gemm_multi(gi, nconv, ident, Lw.col_diag, Lw.w_hi, Lw.w_lo, Lw.cout_pad, Lw.w_ld, ep, exact_ ? 2 : 1,
-                      num_sms_, st, reverse);
+    if (use_patch)
+      launch_conv3x3_patch(in, Lw.g, Lw.w_hi, Lw.w_lo, Lw.w_ld, ep, exact_ ? 2 : 1, num_sms_, st);
+    else
+      launch_gemm_multi(gi, nconv, ident, Lw.col_diag, Lw.w_hi, Lw.w_lo, Lw.cout_pad, Lw.w_ld, ep, exact_ ? 2 : 1,
+                        num_sms_, st, reverse);
   } else {
     ep.alpha = ones_;
     if (res != nullptr) { ep.res_hi = res->hi; ep.res_lo = res->lo; }
@@ -1449,7 +1455,22 @@ static void conv2d_op(const float* x, const float* w, const float* scale, const 
   SMK_CUDA(cudaGetDevice(&dev));
   SMK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   (void)Ho; (void)Wo;
-  if (use_gemm) launch_gemm_conv(in, g, d_whi, d_wlo, cout_pad, ep, exact ? 2 : 1, sms, st);
+  if (use_gemm && patch_conv_mode() != 0 && patch_conv_supported(in, g)) {
+    // the engine runs this geometry on the resident-patch kernel (NHWC split output): same here, then export
+    Act o;
+    o.B = B; o.H = Ho; o.W = Wo; o.C = Cout;
+    SMK_CUDA(cudaMalloc(&o.hi, o.numel() * sizeof(__half)));
+    if (exact) SMK_CUDA(cudaMalloc(&o.lo, o.numel() * sizeof(__half)));
+    Epilogue e2 = ep;
+    e2.out_mode = OUT_NHWC_SPLIT;
+    e2.out_hi = o.hi;
+    e2.out_lo = o.lo;
+    e2.out_f32 = nullptr;
+    launch_conv3x3_patch(in, g, d_whi, d_wlo, (int)K, e2, exact ? 2 : 1, sms, st);
+    launch_split_to_f32(o, out, st);
+    SMK_CUDA(cudaStreamSynchronize(st));
+    cudaFree(o.hi); cudaFree(o.lo);
+  } else if (use_gemm) launch_gemm_conv(in, g, d_whi, d_wlo, cout_pad, ep, exact ? 2 : 1, sms, st);
   else launch_ref_conv(in, g, d_wref, ep, st);
   SMK_CUDA(cudaStreamSynchronize(st));
   cudaFree(in.hi); cudaFree(in.lo); cudaFree(d_whi); cudaFree(d_wlo); cudaFree(d_wref); cudaFree(d_alpha); cudaFree(d_beta);
@@ -1629,6 +1650,36 @@ int sm_warp_affine(const float* src, int32_t src_h, int32_t src_w, const double*
   int ndev = 0;
   SMK_CHECK(cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0, "no CUDA device: siammask_b200 has no CPU fallback");
   smk::launch_warp_affine(src, src_h, src_w, maps, dst, dst_h, dst_w, border_value, B, static_cast<cudaStream_t>(stream));
+  SM_API_END
+}
+
+static smk::TrackerHp to_hp(const sm_tracker_hp* h) {
+  smk::TrackerHp t;
+  t.context_amount = h->context_amount; t.penalty_k = h->penalty_k; t.window_influence = h->window_influence; t.lr = h->lr;
+  t.exemplar_size = h->exemplar_size; t.instance_size = h->instance_size; t.total_stride = h->total_stride;
+  t.base_size = h->base_size; t.out_size = h->out_size; t.reserved = 0;
+  return t;
+}
+
+int sm_tracker_prepare(int32_t B, const double* state, const int32_t* avg_chans, const sm_tracker_hp* hp, int32_t* boxes,
+                       double* target_sz_in_crop, double* aux, void* stream) {
+  SM_API_BEGIN
+  SMK_CHECK(state && avg_chans && hp && boxes && target_sz_in_crop && aux && B >= 1, "bad argument");
+  int ndev = 0;
+  SMK_CHECK(cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0, "no CUDA device: siammask_b200 has no CPU fallback");
+  smk::launch_tracker_prepare(B, state, avg_chans, to_hp(hp), boxes, target_sz_in_crop, aux, static_cast<cudaStream_t>(stream));
+  SM_API_END
+}
+
+int sm_tracker_update(int32_t B, double* state, const float* records, const double* aux, const int32_t* im_wh,
+                      const sm_tracker_hp* hp, int32_t anchor_num, int32_t score_size, double* maps, double* out,
+                      void* stream) {
+  SM_API_BEGIN
+  SMK_CHECK(state && records && aux && im_wh && hp && B >= 1 && score_size >= 1, "bad argument");
+  int ndev = 0;
+  SMK_CHECK(cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0, "no CUDA device: siammask_b200 has no CPU fallback");
+  smk::launch_tracker_update(B, state, records, aux, im_wh, to_hp(hp), anchor_num, score_size, maps, out,
+                             static_cast<cudaStream_t>(stream));
   SM_API_END
 }
 

@@ -706,6 +706,97 @@ __global__ void warp_affine_kernel(const float* __restrict__ src, int sh, int sw
   dst[((size_t)b * dh + y) * dw + x] = v;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident tracker state (tools/test.py:172-200, 239-249, 263-282, 305-315), one thread per stream, float64 like
+// the reference's numpy arithmetic.  state f64 [B][4] = target_pos (x, y), target_sz (w, h).
+//   prepare: the search window of the next frame -> crop box for crop_resize_kernel, target_sz * scale_x for the
+//            selection penalty, and (scale_x, round(s_x), crop_box x0, y0) kept for the update.
+//   update : decoded winner box + score -> lr-smoothed state, clamped to the frame (:305-315); also the forward affine
+//            map of crop_back (:263-275) that pastes the 127x127 (or 63x63) mask back into the frame.
+__device__ __forceinline__ double py_round(double v) { return rint(v); }   // Python round(): half to even
+
+__global__ void tracker_prepare_kernel(int B, const double* __restrict__ state, const int32_t* __restrict__ avg,
+                                       TrackerHp hp, int32_t* __restrict__ boxes, double* __restrict__ tsz,
+                                       double* __restrict__ aux) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double px = state[4 * b], py = state[4 * b + 1], sw = state[4 * b + 2], sh = state[4 * b + 3];
+  const double wc_x = sh + hp.context_amount * (sw + sh);      // :180-181 (names as in the reference)
+  const double hc_x = sw + hp.context_amount * (sw + sh);
+  double s_x = sqrt(wc_x * hc_x);
+  const double scale_x = (double)hp.exemplar_size / s_x;
+  const double d_search = (double)(hp.instance_size - hp.exemplar_size) / 2.0;
+  const double pad = d_search / scale_x;
+  s_x = s_x + 2.0 * pad;
+  const double sxr = py_round(s_x);
+  const double c = (sxr + 1.0) / 2.0;                          // get_subwindow_tracking :71-76
+  int32_t* bx = boxes + 8 * b;
+  bx[0] = (int32_t)py_round(px - c);
+  bx[1] = (int32_t)py_round(py - c);
+  bx[2] = (int32_t)sxr;
+  bx[3] = avg[3 * b]; bx[4] = avg[3 * b + 1]; bx[5] = avg[3 * b + 2];
+  bx[6] = 0; bx[7] = 0;
+  tsz[2 * b] = sw * scale_x;
+  tsz[2 * b + 1] = sh * scale_x;
+  aux[4 * b] = scale_x;
+  aux[4 * b + 1] = sxr;
+  aux[4 * b + 2] = px - sxr / 2.0;                             // crop_box[0], [1] (:187)
+  aux[4 * b + 3] = py - sxr / 2.0;
+}
+
+__global__ void tracker_update_kernel(int B, double* __restrict__ state, const float* __restrict__ rec,
+                                      const double* __restrict__ aux, const int32_t* __restrict__ imsize, TrackerHp hp,
+                                      int A, int R, double* __restrict__ maps, double* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double px = state[4 * b], py = state[4 * b + 1], sw = state[4 * b + 2], sh = state[4 * b + 3];
+  const double scale_x = aux[4 * b], sxr = aux[4 * b + 1], cx0 = aux[4 * b + 2], cy0 = aux[4 * b + 3];
+  const float* r = rec + 8 * b;
+  const float w = r[2], h = r[3], score = r[4];
+  // penalty of the winner in float64 exactly as :214-232 evaluates it (float32 box terms, float64 target terms)
+  const double tw = sw * scale_x, th = sh * scale_x;
+  const double tpad = (tw + th) * 0.5;
+  const double tsz_c = sqrt((tw + tpad) * (th + tpad));
+  const float padf = (w + h) * 0.5f;
+  double sc = (double)sqrtf((w + padf) * (h + padf)) / tsz_c;
+  sc = fmax(sc, 1.0 / sc);
+  double rc = (tw / th) / (double)(w / h);
+  rc = fmax(rc, 1.0 / rc);
+  const double penalty = exp(-(rc * sc - 1.0) * hp.penalty_k);
+  const double lr = penalty * (double)score * hp.lr;            // :241
+  const double p0 = (double)r[0] / scale_x, p1 = (double)r[1] / scale_x, p2 = (double)w / scale_x, p3 = (double)h / scale_x;
+  double res_x = p0 + px, res_y = p1 + py;
+  double res_w = sw * (1.0 - lr) + p2 * lr, res_h = sh * (1.0 - lr) + p3 * lr;
+  const double im_w = imsize[2 * b], im_h = imsize[2 * b + 1];
+  if (maps != nullptr) {
+    // crop_back mapping of the refined / head mask into the frame (:263-282)
+    const int idx = (int)r[7];
+    const int pidx = idx % (R * R);
+    const double delta_y = pidx / R, delta_x = pidx % R;
+    double s = sxr / (double)hp.instance_size;
+    const double sb0 = cx0 + (delta_x - hp.base_size / 2.0) * hp.total_stride * s;
+    const double sb1 = cy0 + (delta_y - hp.base_size / 2.0) * hp.total_stride * s;
+    const double sb2 = s * hp.exemplar_size;
+    s = (double)hp.out_size / sb2;
+    const double bb0 = -sb0 * s, bb1 = -sb1 * s, bb2 = im_w * s, bb3 = im_h * s;
+    const double a = (im_w - 1.0) / bb2, bq = (im_h - 1.0) / bb3;
+    double* m = maps + 6 * b;
+    m[0] = a; m[1] = 0.0; m[2] = -a * bb0;
+    m[3] = 0.0; m[4] = bq; m[5] = -bq * bb1;
+  }
+  (void)A;
+  res_x = fmax(0.0, fmin(im_w, res_x));                         // :305-308
+  res_y = fmax(0.0, fmin(im_h, res_y));
+  res_w = fmax(10.0, fmin(im_w, res_w));
+  res_h = fmax(10.0, fmin(im_h, res_h));
+  state[4 * b] = res_x; state[4 * b + 1] = res_y; state[4 * b + 2] = res_w; state[4 * b + 3] = res_h;
+  if (out != nullptr) {
+    double* o = out + 8 * b;
+    o[0] = res_x; o[1] = res_y; o[2] = res_w; o[3] = res_h; o[4] = (double)score; o[5] = penalty; o[6] = lr; o[7] = (double)r[7];
+  }
+}
+
 // Tiled variant for the 16/32-channel layers (h2, post0, h1): a persistent block stages the weights once, then
 // walks 8x16 output tiles: the (upsampled, summed) input halo of a tile is built in shared memory once, every thread
 // computes 2 horizontally adjacent pixels x CPT output channels out of smem.  Rows are padded to CIN+1 floats so
@@ -928,6 +1019,18 @@ void launch_select(const float* cls, const float* loc, const float* anchors, con
                    int B, int A, int R, double penalty_k, double window_influence, int32_t* best_idx, int32_t* pos,
                    float* rec, cudaStream_t st) {
   select_kernel<<<B, 256, 0, st>>>(cls, loc, anchors, window, tsz, A, R, penalty_k, window_influence, best_idx, pos, rec);
+  SMK_CUDA(cudaGetLastError());
+}
+
+void launch_tracker_prepare(int B, const double* state, const int32_t* avg, const TrackerHp& hp, int32_t* boxes,
+                            double* tsz, double* aux, cudaStream_t st) {
+  tracker_prepare_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, state, avg, hp, boxes, tsz, aux);
+  SMK_CUDA(cudaGetLastError());
+}
+
+void launch_tracker_update(int B, double* state, const float* rec, const double* aux, const int32_t* imsize,
+                           const TrackerHp& hp, int A, int R, double* maps, double* out, cudaStream_t st) {
+  tracker_update_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, state, rec, aux, imsize, hp, A, R, maps, out);
   SMK_CUDA(cudaGetLastError());
 }
 

@@ -32,6 +32,11 @@ CONV_CASES = [
     ("3x3_v2", 2, 512, 15, 128, 3, 1, 1, 1),             # refine v2.0
     ("3x3_v22", 2, 128, 15, 32, 3, 1, 1, 1),             # refine v2.2 (N = 32)
     ("3x3_v0", 1, 64, 61, 16, 3, 1, 1, 1),               # refine v0.0 (N = 16)
+    # resident-patch kernel (conv3x3_patch_sm100.cu): every (channels, size) pair the engine sends there
+    ("3x3_p1_128_31", 3, 128, 31, 128, 3, 1, 1, 1),      # layer2.1-3 conv2 @255 (two k-blocks, PW 32, 4 rows per tile)
+    ("3x3_p1_64_31", 2, 64, 31, 64, 3, 1, 1, 1),         # layer1 conv2 @127 (template)
+    ("3x3_p1_128_15", 2, 128, 15, 128, 3, 1, 1, 1),      # layer2.1-3 conv2 @127 (PW 16, 8 rows per tile, ragged last tile)
+    ("3x3_p1_64_63_b5", 5, 64, 63, 64, 3, 1, 1, 1),      # > 148 tiles: persistent CTAs take a second tile
 ]
 
 
