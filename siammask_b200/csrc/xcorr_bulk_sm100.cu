@@ -37,8 +37,9 @@ __device__ __forceinline__ void named_barrier(int id, int threads) {
 constexpr int KH = 5, KW = 5;
 
 // One task: output rows [r0, r0+NR) x columns [c0, c0+SW) of one plane.  NR/SW are compile-time so the window indices
-// are; `nr`/`nc` (<= NR/SW) clip the last row block / strip (warp-uniform in the G=32 mapping).
-template <int W, int Wo, int NR, int SW>
+// are.  STATIC = the task is exactly NR x SW (no clipping: straight-line code without predicates); otherwise `nr`/`nc`
+// (<= NR/SW) clip the last row block / strip.
+template <int W, int Wo, int NR, int SW, bool STATIC>
 __device__ __forceinline__ void xcorr_task(const float* __restrict__ xp, const float (&kk)[KH][KW], int r0, int c0,
                                            int nr, int nc, float (&acc)[NR][SW]) {
 #pragma unroll
@@ -49,14 +50,14 @@ __device__ __forceinline__ void xcorr_task(const float* __restrict__ xp, const f
   const int ncol_in = nc + KW - 1;
 #pragma unroll
   for (int r = 0; r < NR + KH - 1; ++r) {      // input row r0 + r feeds output rows r0 + r - u
-    if (r < nr + KH - 1) {
+    if (STATIC || r < nr + KH - 1) {
       float xr[SW + KW - 1];
 #pragma unroll
-      for (int c = 0; c < SW + KW - 1; ++c) xr[c] = c < ncol_in ? row[r * W + c] : 0.f;
+      for (int c = 0; c < SW + KW - 1; ++c) xr[c] = (STATIC || c < ncol_in) ? row[r * W + c] : 0.f;
 #pragma unroll
       for (int u = 0; u < KH; ++u) {
         const int i = r - u;
-        if (i >= 0 && i < NR && i < nr) {
+        if (i >= 0 && i < NR && (STATIC || i < nr)) {
 #pragma unroll
           for (int c = 0; c < SW; ++c)
 #pragma unroll
@@ -65,6 +66,17 @@ __device__ __forceinline__ void xcorr_task(const float* __restrict__ xp, const f
       }
     }
   }
+}
+
+template <int Wo, int NR, int SW>
+__device__ __forceinline__ void xcorr_store(float* __restrict__ op, const float (&acc)[NR][SW], int nr, int nc) {
+#pragma unroll
+  for (int i = 0; i < NR; ++i)
+    if (i < nr) {
+#pragma unroll
+      for (int c = 0; c < SW; ++c)
+        if (c < nc) op[i * Wo + c] = acc[i][c];
+    }
 }
 
 // G planes per stage; tasks = NRB row blocks x NST strips per plane; a warp carries 32/G tasks of G planes.
@@ -126,34 +138,46 @@ xcorr_bulk_kernel(const float* __restrict__ x, const float* __restrict__ k, floa
   const int task = warp * TPW + lane / G;                  // warp-uniform when G == 32
   const bool has_task = task < NRB * NST;
   const int rb = has_task ? task / NST : 0, stp = has_task ? task % NST : 0;
-  const int r0 = rb * NR, c0 = stp * SW;
-  const int nr = min(NR, Ho - r0), nc = min(SW, Wo - c0);
+  // balanced split: the first (Ho - NRB*(NR-1)) row blocks have NR rows, the rest NR-1 (25 rows -> 7,6,6,6); same for
+  // the strips (41 columns -> 6,6,6,6,6,6,5)
+  constexpr int R_EXTRA = Ho - NRB * (NR - 1), C_EXTRA = Wo - NST * (SW - 1);
+  static_assert(R_EXTRA >= 1 && R_EXTRA <= NRB && C_EXTRA >= 1 && C_EXTRA <= NST, "balanced task split");
+  const int r0 = rb * (NR - 1) + min(rb, R_EXTRA), c0 = stp * (SW - 1) + min(stp, C_EXTRA);
+  const int nr = NR - 1 + (rb < R_EXTRA ? 1 : 0), nc = SW - 1 + (stp < C_EXTRA ? 1 : 0);
   for (int it = 0; it < my_tiles; ++it) {
     const int s = it & 1;
     const uint32_t ph = (it >> 1) & 1;
     uint8_t* st = smem_x + s * STAGE_BYTES;
     mbar_wait(&full_bar[s], ph);
-    float acc[NR][SW];
+    const float* ks = reinterpret_cast<const float*>(st + IN_BYTES) + plane * (KH * KW);
+    const float* xp = reinterpret_cast<const float*>(st) + plane * (H * W);
+    float* op = reinterpret_cast<float*>(st) + plane * (Ho * Wo) + r0 * Wo + c0;
+    float kk[KH][KW];
     if (has_task) {
-      const float* ks = reinterpret_cast<const float*>(st + IN_BYTES) + plane * (KH * KW);
-      float kk[KH][KW];
 #pragma unroll
       for (int u = 0; u < KH; ++u)
 #pragma unroll
         for (int v = 0; v < KW; ++v) kk[u][v] = ks[u * KW + v];
-      const float* xp = reinterpret_cast<const float*>(st) + plane * (H * W);
-      xcorr_task<W, Wo, NR, SW>(xp, kk, r0, c0, nr, nc, acc);
     }
-    named_barrier(1, NWARPS * 32);                         // every warp has consumed the stage's inputs
-    if (has_task) {
-      float* op = reinterpret_cast<float*>(st) + plane * (Ho * Wo) + r0 * Wo + c0;
-#pragma unroll
-      for (int i = 0; i < NR; ++i)
-        if (i < nr) {
-#pragma unroll
-          for (int c = 0; c < SW; ++c)
-            if (SW == nc || c < nc) op[i * Wo + c] = acc[i][c];
-        }
+    if constexpr (G == 32 && C_EXTRA == NST && NRB * NST == NWARPS) {
+      // the task is warp-uniform and every strip is SW wide: full-size and one-row-short blocks get their own
+      // straight-line code (no predicates)
+      if (nr == NR) {
+        float acc[NR][SW];
+        xcorr_task<W, Wo, NR, SW, true>(xp, kk, r0, c0, NR, SW, acc);
+        named_barrier(1, NWARPS * 32);                     // every warp has consumed the stage's inputs
+        xcorr_store<Wo, NR, SW>(op, acc, NR, SW);
+      } else {
+        float acc[NR - 1][SW];
+        xcorr_task<W, Wo, NR - 1, SW, true>(xp, kk, r0, c0, NR - 1, SW, acc);
+        named_barrier(1, NWARPS * 32);
+        xcorr_store<Wo, NR - 1, SW>(op, acc, NR - 1, SW);
+      }
+    } else {
+      float acc[NR][SW];
+      if (has_task) xcorr_task<W, Wo, NR, SW, false>(xp, kk, r0, c0, nr, nc, acc);
+      named_barrier(1, NWARPS * 32);
+      if (has_task) xcorr_store<Wo, NR, SW>(op, acc, nr, nc);
     }
     fence_proxy_async();                                   // generic-proxy writes -> visible to the bulk store
     __syncwarp();
