@@ -50,7 +50,6 @@ struct PatchParams {
   int tiles_per_img, num_tiles;
   int panel_bytes;         // one plane of one patch buffer incl. slack rows
   int patch_rows;          // (RO+2)*PW
-  int desc_mode;           // 0: base_offset = 0; 1: base_offset = (start >> 7) & 7   (A/B switch, see header)
   Epilogue ep;
 };
 
@@ -63,12 +62,10 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
-// K-major SWIZZLE_128B descriptor whose start may sit on any 128-byte row of the pattern
-__device__ __forceinline__ uint64_t desc_sw128_row(uint32_t addr, int mode) {
-  uint64_t d = umma_desc_kmajor<128>(addr);
-  if (mode == 1) d |= static_cast<uint64_t>((addr >> 7) & 7) << 49;
-  return d;
-}
+// K-major SWIZZLE_128B descriptors: the start may sit on ANY 128-byte row of the swizzle pattern with the
+// descriptor's base_offset field left 0 — measured on B200 (tests/test_gpu_ops.py, cases 3x3_p1*): the hardware applies
+// the XOR to the shared-memory address bits, so a row shift needs no correction (setting base_offset = (addr >> 7) & 7,
+// as the PTX text suggests for unaligned starts, gives wrong results).
 
 template <int CM, int NSPLIT>
 __global__ void __launch_bounds__(P_THREADS, 1) conv3x3_patch_kernel(const __grid_constant__ PatchParams p) {
@@ -88,7 +85,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv3x3_patch_kernel(const __gri
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform for the compiler (role branches stay convergent)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   // zero the slack rows around every panel once (TMA never writes them)
   {
     const int slack = P_SLACK_ROWS * 128;
@@ -116,11 +114,15 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv3x3_patch_kernel(const __gri
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // broadcast through a shuffle so the compiler KNOWS the TMEM base is warp-uniform: tcgen05 operands live in uniform
+  // registers, and a value that merely came out of shared memory makes ptxas wrap every single MMA in a
+  // divergence ("waterfall") loop — ELECT / R2UR / branch per instruction, ~90 clk of issue time per MMA
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const int slack_bytes = P_SLACK_ROWS * 128;
 
-  if (threadIdx.x == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
+    const bool leader = elect_one();
     // units = (tile, k-block) pairs of this CTA in execution order; unit u uses patch buffer u & 1.  The patch of unit
     // u+1 is requested early in unit u (after as many weight tiles as the ring holds, so that waiting for its buffer —
     // freed when unit u-1 retires — never delays the first taps of unit u): it has most of a unit of MMAs to arrive.
@@ -134,11 +136,14 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv3x3_patch_kernel(const __gri
       const int pbuf = u & 1;
       const uint32_t pph = (u >> 1) & 1;
       mbar_wait_guarded(&pempty[pbuf], pph ^ 1);
-      mbar_arrive_expect_tx(&pfull[pbuf], NSPLIT * p.patch_rows * 128);
+      if (leader) {
+        mbar_arrive_expect_tx(&pfull[pbuf], NSPLIT * p.patch_rows * 128);
 #pragma unroll
-      for (int s = 0; s < NSPLIT; ++s)
-        tma_load_4d(smem + (pbuf * NSPLIT + s) * p.panel_bytes + slack_bytes, &p.tmA[s], &pfull[pbuf], kb * 64, -1,
-                    y0 - 1, b);
+        for (int s = 0; s < NSPLIT; ++s)
+          tma_load_4d(smem + (pbuf * NSPLIT + s) * p.panel_bytes + slack_bytes, &p.tmA[s], &pfull[pbuf], kb * 64, -1,
+                      y0 - 1, b);
+      }
+      __syncwarp();
     };
     int bstage = 0;
     uint32_t bphase = 0;
@@ -148,16 +153,23 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv3x3_patch_kernel(const __gri
       for (int tap = 0; tap < 9; ++tap) {
         if (tap == C::B_STAGES && u + 1 < units) issue_patch(u + 1);
         mbar_wait_guarded(&bempty[bstage], bphase ^ 1);
-        mbar_arrive_expect_tx(&bfull[bstage], C::B_STAGE_BYTES);
-        uint8_t* st = bring + bstage * C::B_STAGE_BYTES;
+        if (leader) {
+          mbar_arrive_expect_tx(&bfull[bstage], C::B_STAGE_BYTES);
+          uint8_t* st = bring + bstage * C::B_STAGE_BYTES;
 #pragma unroll
-        for (int s = 0; s < NSPLIT; ++s)
-          tma_load_2d(st + s * C::B_TILE_BYTES, &p.tmB[s], &bfull[bstage], tap * CM + kb * 64, 0);
+          for (int s = 0; s < NSPLIT; ++s)
+            tma_load_2d(st + s * C::B_TILE_BYTES, &p.tmB[s], &bfull[bstage], tap * CM + kb * 64, 0);
+        }
+        __syncwarp();
         if (++bstage == C::B_STAGES) { bstage = 0; bphase ^= 1; }
       }
     }
-  } else if (threadIdx.x == 32) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // The WHOLE warp walks the loop (convergent control flow, all operands provably uniform) and one elected lane issues:
+    // a `threadIdx.x == 32` branch makes ptxas wrap every tcgen05 instruction in a divergence loop.  Descriptors are
+    // built once per tap; the K steps only add 32 B (>> 4) to their address fields.
+    const bool leader = elect_one();
     int unit = 0, bstage = 0, it = 0;
     uint32_t bphase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -181,26 +193,31 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv3x3_patch_kernel(const __gri
           mbar_wait_guarded(&bfull[bstage], bphase);
           tcgen05_fence_after();
           const uint32_t b_hi = smem_u32(bring + bstage * C::B_STAGE_BYTES);
+          const uint64_t da_hi = umma_desc_kmajor<128>(a_hi0 + shift);
+          const uint64_t da_lo = umma_desc_kmajor<128>(a_lo0 + shift);
+          const uint64_t db_hi = umma_desc_kmajor<128>(b_hi);
+          const uint64_t db_lo = umma_desc_kmajor<128>(b_hi + C::B_TILE_BYTES);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t koff = k * 32;
-            const uint64_t da_hi = desc_sw128_row(a_hi0 + shift + koff, p.desc_mode);
-            const uint64_t db_hi = umma_desc_kmajor<128>(b_hi + koff);
-            umma_f16(tmem_d, da_hi, db_hi, idesc, acc_main);
-            acc_main = 1;
-            if constexpr (NSPLIT == 2) {
-              const uint64_t da_lo = desc_sw128_row(a_lo0 + shift + koff, p.desc_mode);
-              const uint64_t db_lo = umma_desc_kmajor<128>(b_hi + C::B_TILE_BYTES + koff);
-              umma_f16(tmem_d + CM, da_lo, db_hi, idesc, acc_lo);
-              acc_lo = 1;
-              umma_f16(tmem_d + CM, da_hi, db_lo, idesc, 1u);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t kadd = static_cast<uint64_t>(k * 2);   // 32 bytes >> 4 in the start-address field
+              umma_f16(tmem_d, da_hi + kadd, db_hi + kadd, idesc, acc_main);
+              acc_main = 1;
+              if constexpr (NSPLIT == 2) {
+                umma_f16(tmem_d + CM, da_lo + kadd, db_hi + kadd, idesc, acc_lo);
+                acc_lo = 1;
+                umma_f16(tmem_d + CM, da_hi + kadd, db_lo + kadd, idesc, 1u);
+              }
+            }
+            umma_commit(&bempty[bstage]);
+            if (tap == 8) {
+              umma_commit(&pempty[pbuf]);                          // patch buffer free once these MMAs retire
+              if (kb == NKB - 1) umma_commit(&tfull[acc]);
             }
           }
-          umma_commit(&bempty[bstage]);
-          if (tap == 8) {
-            umma_commit(&pempty[pbuf]);                          // patch buffer free once these MMAs retire
-            if (kb == NKB - 1) umma_commit(&tfull[acc]);
-          }
+          __syncwarp();
+          acc_main = 1;
+          acc_lo = 1;
           if (++bstage == C::B_STAGES) { bstage = 0; bphase ^= 1; }
         }
       }
@@ -308,7 +325,7 @@ void launch_patch(const PatchParams& p, int num_sms, cudaStream_t st) {
 
 }  // namespace
 
-// SMB200_PATCH3X3: 0 = off (im2col kernel everywhere), 1 = on (default), 2 = on with descriptor base_offset mode 1
+// SMB200_PATCH3X3: 0 = off (im2col kernel everywhere), 1 = on (default)
 int patch_conv_mode() {
   static const int mode = [] { const char* e = getenv("SMB200_PATCH3X3"); return e ? atoi(e) : 1; }();
   return mode;
@@ -336,7 +353,6 @@ void launch_conv3x3_patch(const Act& in, const ConvGeom& g, const __half* w_hi, 
   p.patch_rows = (p.RO + 2) * p.PW;
   p.panel_bytes = (p.patch_rows + 2 * P_SLACK_ROWS) * 128;
   SMK_CHECK(p.panel_bytes % 1024 == 0, "patch panels must keep the 1024-byte swizzle alignment");
-  p.desc_mode = patch_conv_mode() == 2 ? 1 : 0;
   p.ep = ep;
   for (int s = 0; s < nsplit; ++s) {
     const __half* a = s == 0 ? in.hi : in.lo;

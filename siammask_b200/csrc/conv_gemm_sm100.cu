@@ -121,8 +121,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: provably warp-uniform for the compiler, so the role branches below are convergent.
+  // Every role loop is walked by its WHOLE warp and a single elected lane issues the TMA / tcgen05 instructions: their
+  // operands live in uniform registers, and under a `threadIdx.x == k` branch ptxas wraps each of them in a
+  // divergence loop (ELECT / R2UR / BRA per instruction — ~90 clk of issue time per MMA, which capped the 128-wide
+  // exact tiles at ~65 % tensor duty in round 1).
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  const bool leader = elect_one();
   const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;   // position in the CTA pair; 0 = leader
   const int num_tiles = ((p.m_tiles + CG - 1) / CG) * p.n_tiles;
   const int tile0 = blockIdx.x / CG;
@@ -155,9 +161,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
   __syncthreads();
   if constexpr (CG == 2) cluster_sync_all();      // the peer's barriers are initialised before anything signals them
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // broadcast through a shuffle so the compiler KNOWS the TMEM base is warp-uniform: tcgen05 operands live in uniform
+  // registers, and a value that merely came out of shared memory makes ptxas wrap every single MMA in a
+  // divergence ("waterfall") loop — ELECT / R2UR / branch per instruction, ~90 clk of issue time per MMA
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
     // ===================== TMA producer =====================
     // CTA pairs: both producers fill their own smem but signal the LEADER's full barrier, which expects the bytes of
     // both CTAs; each waits on its own empty barrier (the leader's tcgen05.commit is multicast to the pair).
@@ -167,9 +176,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
     auto acquire = [&](uint32_t bytes_per_cta) {
       if constexpr (CG == 2) mbar_wait_guarded(&empty_bar[stage], phase ^ 1);
       else mbar_wait(&empty_bar[stage], phase ^ 1);
-      if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CG * bytes_per_cta);
+      if (rank == 0 && leader) mbar_arrive_expect_tx(&full_bar[stage], CG * bytes_per_cta);
     };
     auto load_2d = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
+      if (!leader) return;
       if constexpr (CG == 2) tma_load_2d_pair(dst, map, full0 + stage * 8, c0, c1);
       else tma_load_2d(dst, map, &full_bar[stage], c0, c1);
     };
@@ -193,6 +203,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
 #pragma unroll
             for (int s = 0; s < NSPLIT; ++s) load_2d(st + s * A_TILE_BYTES, &sg.tmA[s], n0 + kb * BLOCK_K, m0);
             load_2d(st + NSPLIT * A_TILE_BYTES, &p.tmB[0], sg.b_col0 + n0 + kb * BLOCK_K, nb0);
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           continue;
@@ -213,16 +224,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
             } else {
               const int r = tap / sg.KW;
               const int sx = tap - r * sg.KW;
-              if constexpr (CG == 2)
-                tma_load_im2col_4d_pair(a_dst, &sg.tmA[s], full0 + stage * 8, c0, wb, hb, nb,
-                                        static_cast<uint16_t>(sx * sg.dil), static_cast<uint16_t>(r * sg.dil));
-              else
-                tma_load_im2col_4d(a_dst, &sg.tmA[s], &full_bar[stage], c0, wb, hb, nb,
-                                   static_cast<uint16_t>(sx * sg.dil), static_cast<uint16_t>(r * sg.dil));
+              if (leader) {
+                if constexpr (CG == 2)
+                  tma_load_im2col_4d_pair(a_dst, &sg.tmA[s], full0 + stage * 8, c0, wb, hb, nb,
+                                          static_cast<uint16_t>(sx * sg.dil), static_cast<uint16_t>(r * sg.dil));
+                else
+                  tma_load_im2col_4d(a_dst, &sg.tmA[s], &full_bar[stage], c0, wb, hb, nb,
+                                     static_cast<uint16_t>(sx * sg.dil), static_cast<uint16_t>(r * sg.dil));
+              }
             }
             uint8_t* b_dst = st + NSPLIT * A_TILE_BYTES + s * C::B_TILE_BYTES;
             load_2d(b_dst, &p.tmB[s], sg.b_col0 + kb * BLOCK_K, nb0);
           }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -234,7 +248,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (threadIdx.x == 32 && rank == 0) {
+  } else if (warp == 1 && rank == 0) {
     // ===================== MMA issuer (pairs: the leader CTA issues for both) =====================
     constexpr uint32_t idesc = umma_idesc_f16(BLOCK_M * CG, BLOCK_N);
     auto wait_bar = [&](uint64_t* bar, uint32_t parity) {
@@ -270,25 +284,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
           tcgen05_fence_after();
           const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t b_hi = a_hi + NSPLIT * A_TILE_BYTES;
+          // descriptors once per k-block; the K steps add (16 elements * 2 B) >> 4 = 2 to the start-address field
+          const uint64_t da_hi0 = umma_desc_kmajor<C::SWIZZLE>(a_hi);
+          const uint64_t db_hi0 = umma_desc_kmajor<C::SWIZZLE>(b_hi);
+          const uint64_t da_lo0 = umma_desc_kmajor<C::SWIZZLE>(a_hi + A_TILE_BYTES);
+          const uint64_t db_lo0 = umma_desc_kmajor<C::SWIZZLE>(b_hi + C::B_TILE_BYTES);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint32_t koff = k * UMMA_K * 2;   // bytes along K inside the 128B swizzle row
-            const uint64_t da_hi = umma_desc_kmajor<C::SWIZZLE>(a_hi + koff);
-            const uint64_t db_hi = umma_desc_kmajor<C::SWIZZLE>(b_hi + koff);
-            mma(tmem_d, da_hi, db_hi, acc_main);
-            acc_main = 1;
-            if constexpr (NSPLIT == 2) {
-              const uint64_t da_lo = umma_desc_kmajor<C::SWIZZLE>(a_hi + A_TILE_BYTES + koff);
-              mma(tmem_d + BLOCK_N, da_lo, db_hi, acc_lo);
-              acc_lo = 1;
-              if (!ident) {
-                const uint64_t db_lo = umma_desc_kmajor<C::SWIZZLE>(b_hi + C::B_TILE_BYTES + koff);
-                mma(tmem_d + BLOCK_N, da_hi, db_lo, 1u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t kadd = static_cast<uint64_t>(k * UMMA_K * 2 / 16);
+              mma(tmem_d, da_hi0 + kadd, db_hi0 + kadd, acc_main);
+              acc_main = 1;
+              if constexpr (NSPLIT == 2) {
+                mma(tmem_d + BLOCK_N, da_lo0 + kadd, db_hi0 + kadd, acc_lo);
+                acc_lo = 1;
+                if (!ident) mma(tmem_d + BLOCK_N, da_hi0 + kadd, db_lo0 + kadd, 1u);
               }
             }
+            commit(&empty_bar[stage]);                                   // smem slot free once these MMAs retire
+            if (last_seg && kb == nkb - 1) commit(&tfull_bar[acc]);      // accumulator complete
           }
-          commit(&empty_bar[stage]);                                   // smem slot free once these MMAs retire
-          if (last_seg && kb == nkb - 1) commit(&tfull_bar[acc]);      // accumulator complete
+          __syncwarp();
+          acc_main = 1;
+          acc_lo = 1;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -356,7 +374,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
             // the staging buffer was handed to the TMA one chunk ago: wait until that store has read it
-            if (lane == 0) tma_store_wait_read<0>();
+            if (leader) tma_store_wait_read<0>();
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -375,7 +393,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
+            if (leader) {
 #pragma unroll
               for (int s = 0; s < NSPLIT; ++s) tma_store_2d(&p.tmOut[s], buf + s * C::STG_TILE_BYTES, n, m0);
               tma_store_commit();
@@ -383,9 +401,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
           }
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) release_acc(acc);
+          if (leader) release_acc(acc);
         }
-        if (lane == 0) tma_store_wait_all();
+        if (leader) tma_store_wait_all();
         it = -1;   // tiles consumed
       }
     }

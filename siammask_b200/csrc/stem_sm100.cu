@@ -98,8 +98,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) stem_tc_kernel(const __grid_const
   uint64_t* b_bar = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
 
-  const int warp = threadIdx.x >> 5;
+  // shuffle-broadcast warp index + elected issuing lane: see conv_gemm_sm100.cu (keeps tcgen05 / TMA issue convergent)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  const bool leader = elect_one();
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSPLIT; ++i) { tma_prefetch_desc(&p.tmB[i]); tma_prefetch_desc(&p.tmOut[i]); }
@@ -113,15 +115,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) stem_tc_kernel(const __grid_const
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // broadcast through a shuffle so the compiler KNOWS the TMEM base is warp-uniform: tcgen05 operands live in uniform
+  // registers, and a value that merely came out of shared memory makes ptxas wrap every single MMA in a
+  // divergence ("waterfall") loop — ELECT / R2UR / branch per instruction, ~90 clk of issue time per MMA
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
     // resident weights: 3 k-blocks x NSPLIT planes
-    mbar_arrive_expect_tx(b_bar, C::B_BYTES);
-    for (int kb = 0; kb < KBLOCKS; ++kb)
-      for (int s = 0; s < NSPLIT; ++s)
-        tma_load_2d(b_smem + (kb * NSPLIT + s) * B_TILE, &p.tmB[s], b_bar, kb * BK, 0);
-  } else if (threadIdx.x == 32) {
+    if (leader) {
+      mbar_arrive_expect_tx(b_bar, C::B_BYTES);
+      for (int kb = 0; kb < KBLOCKS; ++kb)
+        for (int s = 0; s < NSPLIT; ++s)
+          tma_load_2d(b_smem + (kb * NSPLIT + s) * B_TILE, &p.tmB[s], b_bar, kb * BK, 0);
+    }
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
     mbar_wait(b_bar, 0);
@@ -138,21 +145,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) stem_tc_kernel(const __grid_const
         tcgen05_fence_after();
         const uint32_t a_hi = smem_u32(a_smem + stage * C::STAGE_BYTES);
         const uint32_t b_hi = smem_u32(b_smem + kb * NSPLIT * B_TILE);
+        const uint64_t da_hi0 = umma_desc_kmajor_sw128(a_hi), db_hi0 = umma_desc_kmajor_sw128(b_hi);
+        const uint64_t da_lo0 = umma_desc_kmajor_sw128(a_hi + A_TILE), db_lo0 = umma_desc_kmajor_sw128(b_hi + B_TILE);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < BK / UK; ++k) {
-          const uint32_t koff = k * UK * 2;
-          const uint64_t da_hi = umma_desc_kmajor_sw128(a_hi + koff);
-          const uint64_t db_hi = umma_desc_kmajor_sw128(b_hi + koff);
-          umma_f16(tmem_d, da_hi, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-          if constexpr (NSPLIT == 2) {
-            const uint64_t da_lo = umma_desc_kmajor_sw128(a_hi + A_TILE + koff);
-            const uint64_t db_lo = umma_desc_kmajor_sw128(b_hi + B_TILE + koff);
-            umma_f16(tmem_d + BN, da_lo, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_f16(tmem_d + BN, da_hi, db_lo, idesc, 1u);
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t kadd = static_cast<uint64_t>(k * UK * 2 / 16);     // 32 B per K step in the address field
+            umma_f16(tmem_d, da_hi0 + kadd, db_hi0 + kadd, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (NSPLIT == 2) {
+              umma_f16(tmem_d + BN, da_lo0 + kadd, db_hi0 + kadd, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_f16(tmem_d + BN, da_hi0 + kadd, db_lo0 + kadd, idesc, 1u);
+            }
           }
+          umma_commit(&empty_bar[stage]);
+          if (kb == KBLOCKS - 1) umma_commit(&tfull_bar[acc]);
         }
-        umma_commit(&empty_bar[stage]);
-        if (kb == KBLOCKS - 1) umma_commit(&tfull_bar[acc]);
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -219,7 +227,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) stem_tc_kernel(const __grid_const
         v[j + 2] = fmaxf(fmaf(__uint_as_float(r[j + 2]), al.z, be.z), 0.f);
         v[j + 3] = fmaxf(fmaf(__uint_as_float(r[j + 3]), al.w, be.w), 0.f);
       }
-      if (lane == 0) tma_store_wait_read<0>();
+      if (leader) tma_store_wait_read<0>();
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -238,13 +246,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) stem_tc_kernel(const __grid_const
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
+      if (leader) {
 #pragma unroll
         for (int s = 0; s < NSPLIT; ++s) tma_store_2d(&p.tmOut[s], buf + s * STG_TILE, chunk * 32, tile * BM + quarter * 32);
         tma_store_commit();
       }
     }
-    if (lane == 0) tma_store_wait_all();
+    if (leader) tma_store_wait_all();
   }
 
   tcgen05_fence_before();
