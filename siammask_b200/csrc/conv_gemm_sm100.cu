@@ -796,13 +796,14 @@ void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, i
   // 3x3 convs -10..-17 %, short-K 1x1 layers +8..+35 % slower (they stay on 128 x 128).  32-wide k-blocks (64 B
   // rows) were slower everywhere.  SMB200_EXACT_N256: 0 = never wide, 1 = default rule, 3 = always wide.
   static const int n256 = [] { const char* e = getenv("SMB200_EXACT_N256"); return e ? atoi(e) : 1; }();
+  static const int wide_kb = [] { const char* e = getenv("SMB200_WIDE_KB"); return e ? atoi(e) : 24; }();
   int total_kb = residual != nullptr ? 2 : 0;
   for (int i = 0; i < nconv; ++i) total_kb += convs[i].g.KH * convs[i].g.KW * convs[i].g.Cin / 64;
   // ... and only when the 128 x 128 tiling would fill the machine anyway: small batches (B=1: 64 tiles) are latency
   // bound and want as many CTAs as they can get
   const long long narrow_tiles = (long long)((p.M + BLOCK_M - 1) / BLOCK_M) * (cout_pad / 128);
   const bool wide_exact = nsplit == 2 && cout_pad >= 256 && ep.out_mode == OUT_NHWC_SPLIT &&
-                          (n256 == 3 || (n256 == 1 && total_kb >= 24 && narrow_tiles >= num_sms));
+                          (n256 == 3 || (n256 == 1 && total_kb >= wide_kb && narrow_tiles >= num_sms));
   const int block_n = cout_pad < 256 ? cout_pad : (nsplit == 2 && !wide_exact ? 128 : 256);
   const int bk = 64;
   // CTA pairs (cluster of 2, tcgen05 cta_group::2, 256 x 256 tiles): each CTA stages its own 128 A rows and half of
