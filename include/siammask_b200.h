@@ -65,6 +65,19 @@ int sm_engine_load_weights(sm_engine* e, const sm_tensor_desc* tensors, int32_t 
 int sm_engine_weight_blob(sm_engine* e, void** dev_ptr, size_t* bytes);
 int sm_engine_adopt_weights(sm_engine* e);
 
+/* Static activation scales.  Activations live in HBM as two fp16 planes of value * 2^s (22 significant bits), so
+ * |value * 2^s| must stay below 65504 and well above fp16's subnormals.  Without calibration s = 0 everywhere, which fits
+ * BN-normalised checkpoints (activations O(1)..O(10^3)).  sm_engine_calibrate runs template + track_mask (+ mask head)
+ * + refine on a representative sample batch (z f32 [B,3,127,127], x f32 [B,3,S,S], device; slots 0..B-1 are
+ * overwritten), measures max |value| per tensor and re-packs every layer with per-tensor power-of-two scales chosen
+ * for ~64x headroom: conv + BN is linear and ReLU / max-pool / crops commute with a positive scale, so the scales are
+ * free at run time and results are unchanged.  Needs the weights to have come through sm_engine_load_weights on this
+ * engine; the scales travel inside the weight arena (broadcast / packed file).
+ * sm_engine_status: synchronises and returns flags; bit 0 = some activation left fp16's range since the last calibrate /
+ * engine creation (results invalid: calibrate with representative data). */
+int sm_engine_calibrate(sm_engine* e, int32_t B, const float* z_nchw, const float* x_nchw, void* stream);
+int sm_engine_status(sm_engine* e, int32_t* flags);
+
 /* Custom.template — custom.py:173-174.  z: device f32 [B,3,127,127].  Caches, for slots
  * slot0..slot0+B-1, the template feature and the three conv_kernel outputs (models/rpn.py:64),
  * which the reference recomputes every frame. */

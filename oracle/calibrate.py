@@ -32,9 +32,18 @@ def synthetic_inputs(seed: int, batch: int, search: int = 255):
     return z, x
 
 
-@functools.lru_cache(maxsize=2)
-def calibrated_state_dict(seed: int = 0):
+@functools.lru_cache(maxsize=4)
+def calibrated_state_dict(seed: int = 0, log2_scale: int = 0):
+    """log2_scale != 0: every BN's gamma / beta is multiplied by 2^log2_scale BEFORE the statistics pass, so every
+    activation of the network is ~2^log2_scale times larger (smaller) than in the O(1) fixture — the dynamic-range
+    fixture for the engine's fp16 split activation format."""
     sd = synthetic_state_dict(seed)
+    if log2_scale != 0:
+        f = 2.0 ** log2_scale
+        for k in [k for k in sd if k.endswith(".running_mean")]:
+            base = k[:-len(".running_mean")]
+            sd[base + ".weight"] = sd[base + ".weight"] * f
+            sd[base + ".bias"] = sd[base + ".bias"] * f
     z, x = synthetic_inputs(seed + 1000, 2)
     with torch.no_grad():
         # 1) backbone + ResDownS statistics from the search crops

@@ -45,6 +45,8 @@ SIGNATURES = {
     "sm_engine_load_weights": (C.c_int, [C.c_void_p, C.POINTER(SmTensorDesc), C.c_int32]),
     "sm_engine_weight_blob": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "sm_engine_adopt_weights": (C.c_int, [C.c_void_p]),
+    "sm_engine_calibrate": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sm_engine_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "sm_template": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "sm_track": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                            C.c_int32, C.c_void_p]),

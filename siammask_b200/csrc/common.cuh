@@ -17,6 +17,7 @@ struct Act {
   __half* hi = nullptr;
   __half* lo = nullptr;
   int B = 0, H = 0, W = 0, C = 0;
+  int sexp = 0;                     // host-side metadata: stored value = true value * 2^sexp (static activation scale)
   __host__ __device__ size_t numel() const { return (size_t)B * H * W * C; }
   __host__ __device__ int M() const { return B * H * W; }
 };
@@ -40,7 +41,14 @@ struct Epilogue {
   float* out_f32 = nullptr;       // OUT_NHWC_F32 / OUT_NCHW_F32
   int out_mode = OUT_NHWC_SPLIT;
   int relu = 0;
+  int* ovf = nullptr;             // OUT_NHWC_SPLIT: set to 1 when a value leaves fp16's range (|v| > 65504 or NaN)
 };
+
+// fp16 split planes hold |v| <= 65504: anything larger (or NaN) raises the engine's overflow flag instead of silently
+// becoming inf and poisoning everything downstream (engine.cu: calibrate() picks static power-of-two activation scales)
+__device__ __forceinline__ void flag_if_out_of_range(float absmax, int* ovf) {
+  if (ovf != nullptr && !(absmax <= 65504.f)) atomicOr(ovf, 1);
+}
 
 // One K-segment of the implicit GEMM (see conv_gemm_sm100.cu).
 struct GemmSegment {
@@ -130,7 +138,7 @@ void launch_conv3x3_patch(const Act& in, const ConvGeom& g, const __half* w_hi, 
 
 // stem_sm100.cu : 7x7/2 stem on the tensor cores (weights [64][192] K-major, k = (r*7+s)*3+c, pow2-scaled)
 void launch_stem_tc(const float* x_nchw, int B, int S, const __half* w_hi, const __half* w_lo, const float* alpha,
-                    const float* beta, Act out, int num_sms, cudaStream_t st);
+                    const float* beta, Act out, int num_sms, cudaStream_t st, int* ovf = nullptr);
 
 // simt_kernels.cu
 void launch_ref_conv(const Act& in, const ConvGeom& g, const float* w_krsc_cout, const Epilogue& ep,
@@ -138,8 +146,9 @@ void launch_ref_conv(const Act& in, const ConvGeom& g, const float* w_krsc_cout,
 void launch_stem(const float* x_nchw, int B, int S, const float* w, const float* alpha, const float* beta, Act out,
                  cudaStream_t st);
 void launch_maxpool3s2(const Act& in, Act out, cudaStream_t st);
-void launch_xcorr_nhwc(const Act& x, const __half* k_hi, const __half* k_lo, int kh, int kw, Act out,
-                       cudaStream_t st);
+void launch_xcorr_nhwc(const Act& x, const __half* k_hi, const __half* k_lo, int kh, int kw, Act out, float mul,
+                       int* ovf, cudaStream_t st);
+void launch_absmax(const Act& a, float* slot, cudaStream_t st);
 void launch_xcorr_nchw_f32(const float* x, const float* k, float* out, int planes, int H, int W, int kh, int kw,
                            cudaStream_t st);
 int launch_xcorr_bulk_f32(const float* x, const float* k, float* out, int planes, int H, int W, int kh, int kw,
@@ -147,11 +156,11 @@ int launch_xcorr_bulk_f32(const float* x, const float* k, float* out, int planes
 void launch_crop_center(const Act& in, int crop, Act out, cudaStream_t st);
 void launch_refine_crop(const Act& in, const int32_t* pos, int pos_max, int scale, int padv, int size, Act out,
                         cudaStream_t st);
-void launch_gather_corr(const Act& corr, const int32_t* pos, float* out, cudaStream_t st);
+void launch_gather_corr(const Act& corr, const int32_t* pos, float* out, float mul, cudaStream_t st);
 void launch_gather_mask_col(const float* mask, const int32_t* pos, int B, int C, int R, float* out, cudaStream_t st);
 void launch_deconv(const float* p3, const float* w, const float* bias, float* out, int B, int Cin, int N,
                    int cout, cudaStream_t st);
-void launch_split_to_f32(const Act& in, float* out, cudaStream_t st);
+void launch_split_to_f32(const Act& in, float* out, cudaStream_t st, float mul = 1.f);
 void launch_import_nchw(const float* x_nchw, Act out, cudaStream_t st);
 void launch_warp_affine(const float* src, int sh, int sw, const double* maps, float* dst, int dh, int dw, float border,
                         int B, cudaStream_t st);

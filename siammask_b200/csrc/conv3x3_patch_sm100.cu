@@ -270,6 +270,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv3x3_patch_kernel(const __gri
           for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
         }
         if (ok) {
+          float amax = 0.f;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) amax = fmaxf(amax, fabsf(v[q]));
+          flag_if_out_of_range(amax, ep.ovf);
 #pragma unroll
           for (int q = 0; q < 32; q += 8) {
             uint4 h, l;

@@ -373,6 +373,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
+            {
+              float amax = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(v[j]));
+              flag_if_out_of_range(amax, ep.ovf);
+            }
             // the staging buffer was handed to the TMA one chunk ago: wait until that store has read it
             if (leader) tma_store_wait_read<0>();
             __syncwarp();
@@ -471,6 +477,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
             for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
           }
           if (ep.out_mode == OUT_NHWC_SPLIT) {
+            float amax = 0.f;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) amax = fmaxf(amax, fabsf(v[j]));
+            flag_if_out_of_range(amax, ep.ovf);
             const size_t off = static_cast<size_t>(m) * p.Cout + n;
 #pragma unroll
             for (int j = 0; j < CH; j += 8) {

@@ -47,6 +47,13 @@ struct ConvW {
   float* w_ref = nullptr;
   float* alpha = nullptr;             // pow2 de-scaling of the tensor-core weights
   float* beta = nullptr;              // folded BN shift / conv bias
+  // static power-of-two activation scales (calibrate()): a tensor is STORED as value * 2^s.  s_in / s_in2 / s_res are
+  // the scales of this layer's inputs (first conv, fused second conv, residual), s_out of its output; the weights,
+  // alpha and beta in the arena are packed for exactly these values (quantize_layer).
+  int s_in = 0, s_in2 = 0, s_res = 0, s_out = 0;
+  bool f32_out = false;               // output leaves as fp32 (heads, refine inputs): s_out stays 0
+  std::string src_in, src_in2, src_res;   // producer tensor names, recorded by the calibration pass
+  std::vector<double> shift, shift2;      // unscaled folded shifts (host), kept so the layer can be re-quantized
 };
 
 struct F32T {                         // fp32 NHWC tensor (refine stage)
@@ -96,7 +103,9 @@ class Engine {
   ~Engine() { release(); }
 
   void load_weights(const sm_tensor_desc* t, int n);
-  void adopt_weights() { weights_ready_ = true; }
+  void adopt_weights();
+  void calibrate(int B, const float* z, const float* x, cudaStream_t st);
+  int status();
   void weight_blob(void** p, size_t* bytes) { *p = blob_; *bytes = blob_bytes_; }
 
   void do_template(int slot0, int B, const float* z, cudaStream_t st);
@@ -139,7 +148,17 @@ class Engine {
   void assign_blob_layout();
   size_t measure_arena(int B, int S, bool search);
   // ---- packing
-  void pack_layer(ConvW& L, const std::map<std::string, const sm_tensor_desc*>& sd, uint8_t* host);
+  void fold_layer(ConvW& L, const std::map<std::string, const sm_tensor_desc*>& sd, uint8_t* host);
+  void quantize_layer(ConvW& L, uint8_t* host);
+  void quantize_stem(uint8_t* host);
+  void write_scale_table(uint8_t* host);
+  void read_scale_table(const uint8_t* host);
+  void upload_blob();
+  int tscale(const std::string& name) const {
+    auto it = tscale_.find(name);
+    return it == tscale_.end() ? 0 : it->second;
+  }
+  void note_tensor(const Act& a, const std::string& name, cudaStream_t st);
   // ---- schedule
   Act alloc_act(Arena& ar, int B, int H, int W, int C);
   F32T alloc_f32(Arena& ar, int B, int H, int W, int C);
@@ -179,6 +198,16 @@ class Engine {
   uint8_t* blob_ = nullptr;
   size_t blob_bytes_ = 0;
   bool weights_ready_ = false;
+  std::vector<uint8_t> host_blob_;                       // host image of the arena (kept: re-quantization after calibrate)
+  size_t off_scales_ = 0;
+  std::map<std::string, int> tscale_;                    // scales of tensors that are not conv outputs: stem, corr_*
+  int* ovf_flag_ = nullptr;                              // device: set when an activation left fp16's range
+  // calibration pass: producer name per activation buffer, max |value| per tensor name
+  bool calibrating_ = false;
+  std::unordered_map<const void*, std::string> tensor_name_;
+  std::vector<std::string> absmax_names_;
+  float* absmax_dev_ = nullptr;
+  static constexpr int kAbsmaxSlots = 256;
 
   Arena templ_arena_;
   Lane lanes_[kMaxLanes];
@@ -267,7 +296,7 @@ class Engine {
     // per-launch profiling (bench.py roofline) times every layer as ONE launch over the whole batch: per-kernel
     // durations are not defined while two lanes interleave, and half-batch launches timed back to back would charge
     // each kernel the idle last wave that the other lane fills in the real schedule
-    split_n_ = profiling_ ? 1 : lanes_for(n_lanes_, B);
+    split_n_ = (profiling_ || calibrating_) ? 1 : lanes_for(n_lanes_, B);
     split_off_[0] = 0;
     for (int l = 0; l < split_n_; ++l) {
       split_off_[l + 1] = split_off_[l] + chunk(B, split_n_, l);
@@ -296,7 +325,7 @@ class Engine {
   };
   template <typename F>
   void run_with_graph(const std::vector<uint64_t>& key, cudaStream_t st, F&& body) {
-    if (!use_graphs_ || profiling_) { body(); return; }
+    if (!use_graphs_ || profiling_ || calibrating_) { body(); return; }
     GraphEntry& ge = graphs_[key];
     if (ge.exec != nullptr) {
       SMK_CUDA(cudaGraphLaunch(ge.exec, st));
@@ -342,7 +371,7 @@ class Engine {
     sync_next_ = (sync_next_ + 1) % sync_events_.size();
     return e;
   }
-  bool concurrent() const { return !profiling_; }
+  bool concurrent() const { return !profiling_ && !calibrating_; }
   // make `to` wait for everything enqueued on `from` so far
   void order_after(cudaStream_t from, cudaStream_t to) {
     if (from == to) return;
@@ -476,6 +505,7 @@ void Engine::assign_blob_layout() {
     off_deconv_w_ = off; off = align_up(off + (size_t)256 * 7200 * sizeof(float));
     off_deconv_b_ = off; off = align_up(off + 32 * sizeof(float));
   }
+  off_scales_ = off; off = align_up(off + (layer_order_.size() * 4 + 4) * sizeof(int32_t));
   blob_bytes_ = off;
 }
 
@@ -504,6 +534,8 @@ void Engine::construct(const sm_config& cfg) {
   build_layer_table();
   assign_blob_layout();
   SMK_CUDA(cudaMalloc(&blob_, blob_bytes_));
+  SMK_CUDA(cudaMalloc(&ovf_flag_, sizeof(int)));
+  SMK_CUDA(cudaMemset(ovf_flag_, 0, sizeof(int)));
   for (auto& kv : layers_) {
     ConvW& w = kv.second;
     if (w.gemm_ok) {
@@ -620,6 +652,8 @@ void Engine::release() {
   if (d2h_stream_) cudaStreamDestroy(d2h_stream_);
   cudaFree(maps_dev_);
   cudaFree(mask_raw_);
+  cudaFree(ovf_flag_);
+  cudaFree(absmax_dev_);
   for (auto e : sync_events_) cudaEventDestroy(e);
   for (auto e : event_pool_) cudaEventDestroy(e);
   for (auto& kv : graphs_) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -681,68 +715,139 @@ void fold_affine(const std::map<std::string, const sm_tensor_desc*>& sd, const s
 }
 }  // namespace
 
-void Engine::pack_layer(ConvW& L, const std::map<std::string, const sm_tensor_desc*>& sd, uint8_t* host) {
+// Step 1 of the ingest: BN folding (float64) into fp32 weights [K][Cout] (`w_ref`, also the SIMT backend's operand)
+// and unscaled shifts.  Needs the checkpoint; everything after this works from the host image alone.
+void Engine::fold_layer(ConvW& L, const std::map<std::string, const sm_tensor_desc*>& sd, uint8_t* host) {
+  const ConvGeom& g = L.g;
+  const size_t K = (size_t)g.KH * g.KW * g.Cin;
+  const float* w = find_tensor(sd, L.conv_key + ".weight", K * g.Cout);   // OIHW
+  std::vector<double> scale;
+  fold_affine(sd, L.conv_key, L.bn_key, g.Cout, scale, L.shift);
+  float* w_ref = reinterpret_cast<float*>(host + L.off_wref);
+  const int HW = g.KH * g.KW;
+  for (int n = 0; n < g.Cout; ++n)
+    for (int c = 0; c < g.Cin; ++c)
+      for (int t = 0; t < HW; ++t)
+        w_ref[((size_t)t * g.Cin + c) * g.Cout + n] = (float)((double)w[((size_t)n * g.Cin + c) * HW + t] * scale[n]);
+}
+
+// Step 2: tensor-core operands for the layer's current activation scales.  With inputs stored as a * 2^s_in (a2 * 2^s_in2,
+// r * 2^s_res) the accumulator of output channel n is 2^(e_n + s_in) * sum(w a) when
+//   * the first conv's weights are scaled by 2^e_n (per-channel, keeps hi AND lo fp16 parts normal),
+//   * the fused second conv's by 2^(e_n + s_in - s_in2),
+//   * the residual's diag entry is 2^(e_n + s_in - s_res);
+// the epilogue's alpha = 2^(s_out - s_in - e_n) and beta = shift * 2^s_out then store the output at 2^s_out.
+void Engine::quantize_layer(ConvW& L, uint8_t* host) {
   const ConvGeom& g = L.g;
   const size_t K = (size_t)g.KH * g.KW * g.Cin;
   const size_t K2 = L.fused2 ? (size_t)L.g2.KH * L.g2.KW * L.g2.Cin : 0;
-  const float* w = find_tensor(sd, L.conv_key + ".weight", K * g.Cout);   // OIHW
-  const float* w2 = L.fused2 ? find_tensor(sd, L.conv_key2 + ".weight", K2 * g.Cout) : nullptr;
-  std::vector<double> scale, shift, scale2, shift2;
-  fold_affine(sd, L.conv_key, L.bn_key, g.Cout, scale, shift);
-  if (L.fused2) fold_affine(sd, L.conv_key2, L.bn_key2, g.Cout, scale2, shift2);
-  float* w_ref = reinterpret_cast<float*>(host + L.off_wref);
+  const float* w_ref = reinterpret_cast<const float*>(host + L.off_wref);
+  const ConvW* L2 = L.fused2 ? &layers_.at(L.conv_key2) : nullptr;
+  const float* w_ref2 = L2 ? reinterpret_cast<const float*>(host + L2->off_wref) : nullptr;
   float* alpha = reinterpret_cast<float*>(host + L.off_alpha);
   float* beta = reinterpret_cast<float*>(host + L.off_beta);
   float* beta2 = reinterpret_cast<float*>(host + L.off_beta2);
   __half* w_hi = L.gemm_ok ? reinterpret_cast<__half*>(host + L.off_whi) : nullptr;
   __half* w_lo = L.gemm_ok ? reinterpret_cast<__half*>(host + L.off_wlo) : nullptr;
   for (int n = 0; n < L.cout_pad; ++n) { alpha[n] = 0.f; beta[n] = 0.f; beta2[n] = 0.f; }
-  const int HW = g.KH * g.KW, HW2 = L.fused2 ? L.g2.KH * L.g2.KW : 0;
   const size_t ld = (size_t)L.w_ld;
-  std::vector<float> row2(K2);
+  const int d2 = L.s_in - L.s_in2;                  // relative scale of the fused second conv's weights
   for (int n = 0; n < g.Cout; ++n) {
-    // folded weight rows (fp32) and their largest magnitude
     float amax = 0.f;
-    for (int c = 0; c < g.Cin; ++c)
-      for (int t = 0; t < HW; ++t) {
-        const float fw = (float)((double)w[((size_t)n * g.Cin + c) * HW + t] * scale[n]);
-        w_ref[((size_t)t * g.Cin + c) * g.Cout + n] = fw;
-        amax = std::max(amax, std::fabs(fw));
-      }
-    for (int c = 0; c < (L.fused2 ? L.g2.Cin : 0); ++c)
-      for (int t = 0; t < HW2; ++t) {
-        const float fw = (float)((double)w2[((size_t)n * L.g2.Cin + c) * HW2 + t] * scale2[n]);
-        row2[(size_t)t * L.g2.Cin + c] = fw;
-        amax = std::max(amax, std::fabs(fw));
-      }
-    beta[n] = (float)shift[n];
-    beta2[n] = (float)(shift[n] + (L.fused2 ? shift2[n] : 0.0));
-    alpha[n] = 1.f;
-    if (L.gemm_ok) {
-      // per-output-channel power-of-two scaling keeps hi AND lo fp16 parts in the normal range; the epilogue
-      // multiplies the accumulator back by 2^-e (exact).  |e| <= 14 so 2^e itself is a normal fp16 (diag block).
-      int e = 0;
-      if (amax > 0.f) e = (int)std::floor(std::log2(16384.0 / (double)amax));
-      e = std::max(-14, std::min(14, e));
-      alpha[n] = std::ldexp(1.f, -e);
-      __half* rh = w_hi + (size_t)n * ld;
-      __half* rl = w_lo + (size_t)n * ld;
-      for (int c = 0; c < g.Cin; ++c)
-        for (int t = 0; t < HW; ++t) {
-          const float fw = std::ldexp(w_ref[((size_t)t * g.Cin + c) * g.Cout + n], e);
-          const __half h = __float2half_rn(fw);
-          rh[(size_t)t * g.Cin + c] = h;
-          rl[(size_t)t * g.Cin + c] = __float2half_rn(fw - __half2float(h));
-        }
-      for (size_t k = 0; k < K2; ++k) {
-        const float fw = std::ldexp(row2[k], e);
-        const __half h = __float2half_rn(fw);
-        rh[L.col2 + k] = h;
-        rl[L.col2 + k] = __float2half_rn(fw - __half2float(h));
-      }
-      if (L.has_diag) rh[L.col_diag + n] = __float2half_rn(std::ldexp(1.f, e));   // rest of the block stays 0
+    for (size_t k = 0; k < K; ++k) amax = std::max(amax, std::fabs(w_ref[k * g.Cout + n]));
+    for (size_t k = 0; k < K2; ++k) amax = std::max(amax, std::fabs(std::ldexp(w_ref2[k * g.Cout + n], d2)));
+    beta[n] = (float)std::ldexp(L.shift[n], L.s_out);
+    beta2[n] = (float)std::ldexp(L.shift[n] + (L2 ? L2->shift[n] : 0.0), L.s_out);
+    alpha[n] = std::ldexp(1.f, L.s_out - L.s_in);
+    if (!L.gemm_ok) continue;
+    // per-output-channel power-of-two scaling keeps hi AND lo fp16 parts in the normal range; |e| <= 14, and with a
+    // residual the diag entry 2^(e + s_in - s_res) must itself be a normal fp16
+    int e = 0;
+    if (amax > 0.f) e = (int)std::floor(std::log2(16384.0 / (double)amax));
+    e = std::max(-14, std::min(14, e));
+    if (L.has_diag) {
+      const int d = L.s_in - L.s_res;
+      e = std::max(-14 - d, std::min(14 - d, e));
+      SMK_CHECK(e >= -24 && e <= 24, "activation scales of a residual block are too far apart");
+    }
+    alpha[n] = std::ldexp(1.f, L.s_out - L.s_in - e);
+    __half* rh = w_hi + (size_t)n * ld;
+    __half* rl = w_lo + (size_t)n * ld;
+    for (size_t k = 0; k < K; ++k) {
+      const float fw = std::ldexp(w_ref[k * g.Cout + n], e);
+      const __half h = __float2half_rn(fw);
+      rh[k] = h;
+      rl[k] = __float2half_rn(fw - __half2float(h));
+    }
+    for (size_t k = 0; k < K2; ++k) {
+      const float fw = std::ldexp(w_ref2[k * g.Cout + n], e + d2);
+      const __half h = __float2half_rn(fw);
+      rh[L.col2 + k] = h;
+      rl[L.col2 + k] = __float2half_rn(fw - __half2float(h));
+    }
+    if (L.has_diag) rh[L.col_diag + n] = __float2half_rn(std::ldexp(1.f, e + L.s_in - L.s_res));   // rest stays 0
+  }
+}
+
+// tensor-core stem: [64][192] K-major, k = (r*7+s)*3 + c — exactly the row index of the folded w_ref; output at 2^s
+void Engine::quantize_stem(uint8_t* host) {
+  ConvW& stem = layers_["features.features.conv1"];
+  const int s_out = tscale("stem");
+  stem.s_out = s_out;
+  const float* wref = reinterpret_cast<const float*>(host + stem.off_wref);
+  __half* sh = reinterpret_cast<__half*>(host + off_stem_whi_);
+  __half* sl = reinterpret_cast<__half*>(host + off_stem_wlo_);
+  float* sa = reinterpret_cast<float*>(host + off_stem_alpha_);
+  float* sb = reinterpret_cast<float*>(host + stem.off_beta);
+  for (int n = 0; n < 64; ++n) {
+    float amax = 0.f;
+    for (int k = 0; k < 147; ++k) amax = std::max(amax, std::fabs(wref[(size_t)k * 64 + n]));
+    int e = amax > 0.f ? (int)std::floor(std::log2(16384.0 / (double)amax)) : 0;
+    e = std::max(-14, std::min(14, e));
+    sa[n] = std::ldexp(1.f, s_out - e);
+    sb[n] = (float)std::ldexp(stem.shift[n], s_out);
+    for (int k = 0; k < 147; ++k) {
+      const float fw = std::ldexp(wref[(size_t)k * 64 + n], e);
+      const __half h = __float2half_rn(fw);
+      sh[n * 192 + k] = h;
+      sl[n * 192 + k] = __float2half_rn(fw - __half2float(h));
     }
   }
+}
+
+// the scales travel with the arena (NCCL broadcast / packed-weight file): 4 ints per layer + the named tensors
+static const char* kNamedTensors[4] = {"stem", "corr_cls", "corr_loc", "corr_mask"};
+void Engine::write_scale_table(uint8_t* host) {
+  int32_t* t = reinterpret_cast<int32_t*>(host + off_scales_);
+  size_t i = 0;
+  for (const auto& k : layer_order_) {
+    const ConvW& w = layers_[k];
+    t[i++] = w.s_in; t[i++] = w.s_in2; t[i++] = w.s_res; t[i++] = w.s_out;
+  }
+  for (const char* nm : kNamedTensors) t[i++] = tscale(nm);
+}
+void Engine::read_scale_table(const uint8_t* host) {
+  const int32_t* t = reinterpret_cast<const int32_t*>(host + off_scales_);
+  size_t i = 0;
+  for (const auto& k : layer_order_) {
+    ConvW& w = layers_[k];
+    w.s_in = t[i++]; w.s_in2 = t[i++]; w.s_res = t[i++]; w.s_out = t[i++];
+  }
+  for (const char* nm : kNamedTensors) tscale_[nm] = t[i++];
+}
+
+void Engine::upload_blob() {
+  write_scale_table(host_blob_.data());
+  SMK_CUDA(cudaMemcpy(blob_, host_blob_.data(), blob_bytes_, cudaMemcpyHostToDevice));
+}
+
+// weights arrived by broadcast / from a packed file: take the activation scales from the arena
+void Engine::adopt_weights() {
+  std::vector<uint8_t> tbl(blob_bytes_ - off_scales_);
+  SMK_CUDA(cudaMemcpy(tbl.data(), blob_ + off_scales_, tbl.size(), cudaMemcpyDeviceToHost));
+  read_scale_table(tbl.data() - off_scales_);
+  host_blob_.clear();                 // no host image: calibrate() needs load_weights on this engine
+  weights_ready_ = true;
 }
 
 void Engine::load_weights(const sm_tensor_desc* t, int n) {
@@ -753,43 +858,139 @@ void Engine::load_weights(const sm_tensor_desc* t, int n) {
     if (name.rfind("module.", 0) == 0) name = name.substr(7);   // utils/load_helper.py:22-27
     sd[name] = &t[i];
   }
-  std::vector<uint8_t> host(blob_bytes_, 0);
-  for (const auto& k : layer_order_) pack_layer(layers_[k], sd, host.data());
-  float* ones = reinterpret_cast<float*>(host.data() + off_ones_);
-  for (int i = 0; i < 4096; ++i) ones[i] = 1.f;
-  {
-    // tensor-core stem: [64][192] K-major, k = (r*7+s)*3 + c — exactly the row index of the folded w_ref
-    const ConvW& stem = layers_["features.features.conv1"];
-    const float* wref = reinterpret_cast<const float*>(host.data() + stem.off_wref);
-    __half* sh = reinterpret_cast<__half*>(host.data() + off_stem_whi_);
-    __half* sl = reinterpret_cast<__half*>(host.data() + off_stem_wlo_);
-    float* sa = reinterpret_cast<float*>(host.data() + off_stem_alpha_);
-    for (int n = 0; n < 64; ++n) {
-      float amax = 0.f;
-      for (int k = 0; k < 147; ++k) amax = std::max(amax, std::fabs(wref[(size_t)k * 64 + n]));
-      int e = amax > 0.f ? (int)std::floor(std::log2(16384.0 / (double)amax)) : 0;
-      e = std::max(-14, std::min(14, e));
-      sa[n] = std::ldexp(1.f, -e);
-      for (int k = 0; k < 147; ++k) {
-        const float fw = std::ldexp(wref[(size_t)k * 64 + n], e);
-        const __half h = __float2half_rn(fw);
-        sh[n * 192 + k] = h;
-        sl[n * 192 + k] = __float2half_rn(fw - __half2float(h));
-      }
-    }
+  host_blob_.assign(blob_bytes_, 0);
+  uint8_t* host = host_blob_.data();
+  tscale_.clear();
+  for (const auto& k : layer_order_) {
+    ConvW& w = layers_[k];
+    w.s_in = w.s_in2 = w.s_res = w.s_out = 0;
+    fold_layer(w, sd, host);
   }
+  for (const auto& k : layer_order_) quantize_layer(layers_[k], host);
+  float* ones = reinterpret_cast<float*>(host + off_ones_);
+  for (int i = 0; i < 4096; ++i) ones[i] = 1.f;
+  quantize_stem(host);
   if (cfg_.with_mask) {
     // ConvTranspose2d weight (Cin=256, Cout=32, 15, 15) -> [k][(y*15+x)*32 + co]
     const float* dw = find_tensor(sd, "refine_model.deconv.weight", (size_t)256 * 32 * 225);
     const float* db = find_tensor(sd, "refine_model.deconv.bias", 32);
-    float* wd = reinterpret_cast<float*>(host.data() + off_deconv_w_);
+    float* wd = reinterpret_cast<float*>(host + off_deconv_w_);
     for (int k = 0; k < 256; ++k)
       for (int co = 0; co < 32; ++co)
         for (int p = 0; p < 225; ++p) wd[(size_t)k * 7200 + p * 32 + co] = dw[((size_t)k * 32 + co) * 225 + p];
-    std::memcpy(host.data() + off_deconv_b_, db, 32 * sizeof(float));
+    std::memcpy(host + off_deconv_b_, db, 32 * sizeof(float));
   }
-  SMK_CUDA(cudaMemcpy(blob_, host.data(), blob_bytes_, cudaMemcpyHostToDevice));
+  upload_blob();
   weights_ready_ = true;
+}
+
+
+// Static activation scales.  Every activation lives in HBM as two fp16 planes of value * 2^s (hi + lo, 22 significant
+// bits) — fp16's exponent range is narrow: |value * 2^s| must stay below 65504, and `lo` keeps full precision only
+// while `hi` stays above ~2^-3.  calibrate() runs the whole path (template, track_mask incl. the mask head, refine) on
+// a sample batch, measures max |value| of every tensor and picks s per tensor so that the maximum sits near 2^10
+// (64x headroom above the sample, full lo precision down to 2^-13 of the maximum); the weights / alpha / beta of every
+// layer are then re-quantized for those scales (quantize_layer).  conv+BN is linear and ReLU / max-pool / crops commute
+// with a positive scale, so this costs nothing at run time.  Without calibration all scales are 0: fine for networks
+// whose activations are O(1)..O(10^3) (BN-normalised checkpoints); the overflow flag (status()) tells otherwise.
+void Engine::calibrate(int B, const float* z, const float* x, cudaStream_t st) {
+  SMK_CHECK(weights_ready_ && !host_blob_.empty(), "calibrate() needs weights loaded through sm_engine_load_weights on this engine");
+  SMK_CHECK(cfg_.backend == SM_BACKEND_TENSOR, "calibrate() applies to the tensor-core backend");
+  SMK_CHECK(B >= 1 && B <= cfg_.max_batch && z != nullptr && x != nullptr, "calibration batch");
+  join_lanes(st);
+  const size_t A = cfg_.anchor_num, RR = (size_t)R_ * R_;
+  float *cls = nullptr, *loc = nullptr, *mask = nullptr, *ref = nullptr;
+  int32_t* pos = nullptr;
+  struct Tmp { std::vector<void*> p; ~Tmp() { for (void* q : p) cudaFree(q); } } tmp;
+  auto dalloc = [&](size_t bytes) { void* q = nullptr; SMK_CUDA(cudaMalloc(&q, bytes)); tmp.p.push_back(q); return q; };
+  cls = static_cast<float*>(dalloc(B * 2 * A * RR * sizeof(float)));
+  loc = static_cast<float*>(dalloc(B * 4 * A * RR * sizeof(float)));
+  if (cfg_.with_mask) {
+    mask = static_cast<float*>(dalloc((size_t)B * 3969 * RR * sizeof(float)));
+    ref = static_cast<float*>(dalloc((size_t)B * 127 * 127 * sizeof(float)));
+    pos = static_cast<int32_t*>(dalloc((size_t)B * 2 * sizeof(int32_t)));
+    std::vector<int32_t> hp((size_t)B * 2, R_ / 2);
+    SMK_CUDA(cudaMemcpy(pos, hp.data(), hp.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  if (absmax_dev_ == nullptr) SMK_CUDA(cudaMalloc(&absmax_dev_, kAbsmaxSlots * sizeof(float)));
+  for (auto& kv : graphs_) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  graphs_.clear();                                   // replayed graphs bake the old scale factors into kernel arguments
+
+  auto scale_of = [&](const std::string& name) -> int {
+    auto it = layers_.find(name);
+    return it != layers_.end() ? it->second.s_out : tscale(name);
+  };
+  auto set_scale = [&](const std::string& name, int v) {
+    auto it = layers_.find(name);
+    if (it != layers_.end()) it->second.s_out = it->second.f32_out ? 0 : v;
+    else tscale_[name] = v;
+  };
+  auto rewire_and_upload = [&]() {
+    for (auto& kv : layers_) {
+      ConvW& w = kv.second;
+      if (!w.src_in.empty()) w.s_in = scale_of(w.src_in);
+      if (!w.src_in2.empty()) w.s_in2 = scale_of(w.src_in2);
+      if (!w.src_res.empty()) w.s_res = scale_of(w.src_res);
+    }
+    for (const auto& k : layer_order_) quantize_layer(layers_[k], host_blob_.data());
+    quantize_stem(host_blob_.data());
+    upload_blob();
+  };
+
+  bool settled = false;
+  for (int iter = 0; iter < 12 && !settled; ++iter) {
+    SMK_CUDA(cudaMemsetAsync(absmax_dev_, 0, kAbsmaxSlots * sizeof(float), st));
+    SMK_CUDA(cudaMemsetAsync(ovf_flag_, 0, sizeof(int), st));
+    struct Guard { Engine* e; ~Guard() { e->calibrating_ = false; e->tensor_name_.clear(); } } guard{this};
+    calibrating_ = true;
+    absmax_names_.clear();
+    tensor_name_.clear();
+    do_template(0, B, z, st);
+    if (cfg_.with_mask) {
+      do_track(0, B, x, cls, loc, mask, SM_TRACK_MASK_FEATURES | SM_TRACK_MASK_HEAD, st);
+      do_refine(B, pos, ref, st);
+    } else {
+      do_track(0, B, x, cls, loc, nullptr, 0, st);
+    }
+    SMK_CUDA(cudaStreamSynchronize(st));
+    calibrating_ = false;
+    std::vector<float> mx(absmax_names_.size());
+    SMK_CUDA(cudaMemcpy(mx.data(), absmax_dev_, mx.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    bool any_inf = false, any_zero = false;
+    for (float v : mx) {
+      if (!(v <= 65504.f)) any_inf = true;
+      if (v == 0.f) any_zero = true;
+    }
+    if (any_inf || (any_zero && iter < 8)) {
+      // out of range somewhere: everything downstream of it is meaningless — move ALL scales and look again
+      const int step = any_inf ? -10 : +10;
+      for (size_t i = 0; i < mx.size(); ++i) set_scale(absmax_names_[i], scale_of(absmax_names_[i]) + step);
+      rewire_and_upload();
+      continue;
+    }
+    settled = true;
+    for (size_t i = 0; i < mx.size(); ++i) {
+      if (mx[i] == 0.f) continue;
+      const int cur = scale_of(absmax_names_[i]);
+      // stored maximum already in [2^8, 2^12]: leave the tensor alone (a well-scaled checkpoint keeps s = 0 and its
+      // results bit for bit); otherwise re-target the stored maximum to ~2^10
+      if (mx[i] >= 256.f && mx[i] <= 4096.f) continue;
+      int want = cur + (int)std::lround(std::log2(1024.0 / (double)mx[i]));
+      want = std::max(-60, std::min(60, want));
+      const auto it = layers_.find(absmax_names_[i]);
+      if (it != layers_.end() && it->second.f32_out) want = 0;
+      if (want != cur) { set_scale(absmax_names_[i], want); settled = false; }
+    }
+    if (!settled) rewire_and_upload();
+  }
+  SMK_CHECK(settled, "calibrate(): activation scales did not settle (non-finite network outputs?)");
+}
+
+int Engine::status() {
+  int v = 0;
+  SMK_CUDA(cudaDeviceSynchronize());
+  SMK_CUDA(cudaMemcpy(&v, ovf_flag_, sizeof(int), cudaMemcpyDeviceToHost));
+  return v;
 }
 
 // ================================================================================================
@@ -820,6 +1021,22 @@ void Engine::conv_into(const Act& in, const ConvW& Lw, Epilogue ep, cudaStream_t
   const bool tc = cfg_.backend == SM_BACKEND_TENSOR && Lw.gemm_ok;
   SMK_CHECK(in2 == nullptr || (tc && Lw.fused2), "fused second input needs the tensor-core path");
   if (in2 != nullptr) K += (double)Lw.g2.KH * Lw.g2.KW * Lw.g2.Cin;
+  if (calibrating_) {
+    // record which tensors feed this layer (the scales of a layer's operands are those of their producers)
+    ConvW& W = const_cast<ConvW&>(Lw);
+    auto name_of = [&](const Act& a) {
+      auto it = tensor_name_.find(a.hi);
+      return it == tensor_name_.end() ? std::string() : it->second;
+    };
+    W.src_in = name_of(in);
+    W.src_in2 = in2 ? name_of(*in2) : std::string();
+    W.src_res = res ? name_of(*res) : std::string();
+    W.f32_out = ep.out_mode != OUT_NHWC_SPLIT;
+  }
+  SMK_CHECK(in.sexp == Lw.s_in && (in2 == nullptr || in2->sexp == Lw.s_in2) && (res == nullptr || res->sexp == Lw.s_res),
+            "activation scale mismatch at " + Lw.conv_key + " (weights were packed for other scales: re-run calibrate)");
+  SMK_CHECK(ep.out_mode == OUT_NHWC_SPLIT || Lw.s_out == 0, "fp32 outputs are unscaled");
+  if (ep.out_mode == OUT_NHWC_SPLIT) ep.ovf = ovf_flag_;
   Scope sc(this, Lw.conv_key, tc ? "conv_gemm" : "conv_simt", 2.0 * M * K * Lw.g.Cout,
            4.0 * ((double)in.numel() + (in2 ? (double)in2->numel() : 0.0) + M * Lw.g.Cout * (res ? 2 : 1) +
                   K * Lw.g.Cout), st);
@@ -856,10 +1073,25 @@ void Engine::conv_into(const Act& in, const ConvW& Lw, Epilogue ep, cudaStream_t
       launch_gemm_multi(gi, nconv, ident, Lw.col_diag, Lw.w_hi, Lw.w_lo, Lw.cout_pad, Lw.w_ld, ep, exact_ ? 2 : 1,
                         num_sms_, st, reverse);
   } else {
+    SMK_CHECK(Lw.s_in == 0 && Lw.s_out == 0, "the SIMT backend runs unscaled activations only");
     ep.alpha = ones_;
     if (res != nullptr) { ep.res_hi = res->hi; ep.res_lo = res->lo; }
     launch_ref_conv(in, Lw.g, Lw.w_ref, ep, st);
   }
+}
+
+// calibration pass: remember which tensor lives in this buffer and fold its max |value| into the tensor's slot
+void Engine::note_tensor(const Act& a, const std::string& name, cudaStream_t st) {
+  if (!calibrating_ || measuring_) return;
+  tensor_name_[a.hi] = name;
+  size_t slot = 0;
+  for (; slot < absmax_names_.size(); ++slot)
+    if (absmax_names_[slot] == name) break;
+  if (slot == absmax_names_.size()) {
+    SMK_CHECK((int)slot < kAbsmaxSlots, "too many calibrated tensors");
+    absmax_names_.push_back(name);
+  }
+  launch_absmax(a, absmax_dev_ + slot, st);
 }
 
 Act Engine::conv(const Act& in, const ConvW& Lw, bool relu, const Act* res, Arena& ar, cudaStream_t st,
@@ -870,7 +1102,9 @@ Act Engine::conv(const Act& in, const ConvW& Lw, bool relu, const Act* res, Aren
   ep.out_mode = OUT_NHWC_SPLIT;
   ep.out_hi = out.hi;
   ep.out_lo = out.lo;
+  out.sexp = Lw.s_out;
   conv_into(in, Lw, ep, st, res, in2);
+  note_tensor(out, Lw.conv_key, st);
   return out;
 }
 
@@ -892,12 +1126,17 @@ Act Engine::backbone(const float* x, int B, int S, Arena& ar, bool keep, cudaStr
   const ConvW& stem = L(F + "conv1");
   if (!measuring_) {
     Scope sc(this, "stem", "stem", 2.0 * B * So * So * 64 * 147, 4.0 * B * (3.0 * S * S + 64.0 * So * So), st);
-    if (cfg_.backend == SM_BACKEND_TENSOR) launch_stem_tc(x, B, S, stem_whi_, stem_wlo_, stem_alpha_, stem.beta, p0, num_sms_, st);
+    if (cfg_.backend == SM_BACKEND_TENSOR)
+      launch_stem_tc(x, B, S, stem_whi_, stem_wlo_, stem_alpha_, stem.beta, p0, num_sms_, st, ovf_flag_);
     else launch_stem(x, B, S, stem.w_ref, ones_, stem.beta, p0, st);
     ++launches_;
   }
+  p0.sexp = stem.s_out;
+  note_tensor(p0, "stem", st);
   const int Sp = (So + 2 - 3) / 2 + 1;
   Act y = alloc_act(ar, B, Sp, Sp, 64);
+  y.sexp = p0.sexp;                    // max-pool commutes with a positive scale
+  if (calibrating_ && !measuring_) tensor_name_[y.hi] = "stem";
   if (!measuring_) {
     Scope sc(this, "maxpool", "pool", 0, 4.0 * (p0.numel() + y.numel()), st);
     launch_maxpool3s2(p0, y, st);
@@ -927,6 +1166,8 @@ Act Engine::backbone(const float* x, int B, int S, Arena& ar, bool keep, cudaStr
   Act xf = conv(y, L("features.downsample.downsample.0"), false, nullptr, ar, st);
   if (xf.W < 20) {   // custom.py:21-24
     Act c = alloc_act(ar, B, xf.H - 8, xf.W - 8, xf.C);
+    c.sexp = xf.sexp;
+    if (calibrating_ && !measuring_) tensor_name_[c.hi] = tensor_name_[xf.hi];
     if (!measuring_) { launch_crop_center(xf, 4, c, st); ++launches_; }
     xf = c;
   }
@@ -954,6 +1195,11 @@ void Engine::do_template(int slot0, int B, const float* z, cudaStream_t st) {
     ep.out_hi = kcache_hi_ + off;
     ep.out_lo = exact_ ? kcache_lo_ + off : nullptr;
     conv_into(zf, ck, ep, st);
+    if (calibrating_) {
+      Act kc;
+      kc.hi = ep.out_hi; kc.lo = ep.out_lo; kc.B = B; kc.H = 5; kc.W = 5; kc.C = 256;
+      note_tensor(kc, ck.conv_key, st);
+    }
   }
 }
 
@@ -1018,10 +1264,14 @@ void Engine::track_lane(int slot0, int B, const float* x, float* cls, float* loc
     {
       Scope sc(this, std::string(kCorrName[br]), "xcorr", 2.0 * 25 * corr.numel(),
                4.0 * (cs.numel() + corr.numel() + (double)B * 25 * 256), bs);
-      launch_xcorr_nhwc(cs, kcache_hi_ + off, exact_ ? kcache_lo_ + off : nullptr, 5, 5, corr, bs);
+      corr.sexp = tscale(kCorrName[br]);
+      const int s_kc = L(P + "conv_kernel.0").s_out;
+      launch_xcorr_nhwc(cs, kcache_hi_ + off, exact_ ? kcache_lo_ + off : nullptr, 5, 5, corr,
+                        std::ldexp(1.f, corr.sexp - cs.sexp - s_kc), ovf_flag_, bs);
       ++launches_;
       last_end_[corr.hi] = +1;
     }
+    note_tensor(corr, kCorrName[br], bs);
     cur_->named[kCorrName[br]] = corr;
     if (!(br == 2 && !want_mask_head)) {
       Act h = conv(corr, L(P + "head.0"), true, nullptr, search_arena, bs);
@@ -1097,6 +1347,8 @@ void Engine::refine_lane(int B, const int32_t* pos, float* out, cudaStream_t st)
   {
     Scope sc(this, "crop_p2", "refine_misc", 0, 8.0 * c2.numel(), s2);
     last_end_[c2.hi] = +1;
+    c2.sexp = p2.sexp;
+    if (calibrating_) tensor_name_[c2.hi] = tensor_name_[p2.hi];
     launch_refine_crop(p2, pos, R_ - 1, 1, 4, 15, c2, s2); ++launches_;
   }
   Act v2a = conv(c2, L(R + "v2.0"), true, nullptr, ar, s2);
@@ -1106,6 +1358,8 @@ void Engine::refine_lane(int B, const int32_t* pos, float* out, cudaStream_t st)
   {
     Scope sc(this, "crop_p1", "refine_misc", 0, 8.0 * c1.numel(), s1);
     last_end_[c1.hi] = +1;
+    c1.sexp = p1.sexp;
+    if (calibrating_) tensor_name_[c1.hi] = tensor_name_[p1.hi];
     launch_refine_crop(p1, pos, R_ - 1, 2, 8, 31, c1, s1); ++launches_;
   }
   Act v1a = conv(c1, L(R + "v1.0"), true, nullptr, ar, s1);
@@ -1115,6 +1369,8 @@ void Engine::refine_lane(int B, const int32_t* pos, float* out, cudaStream_t st)
   {
     Scope sc(this, "crop_p0", "refine_misc", 0, 8.0 * c0.numel(), s0);
     last_end_[c0.hi] = +1;
+    c0.sexp = p0.sexp;
+    if (calibrating_) tensor_name_[c0.hi] = tensor_name_[p0.hi];
     launch_refine_crop(p0, pos, R_ - 1, 4, 16, 61, c0, s0); ++launches_;
   }
   F32T v0a = conv_f32(c0, L(R + "v0.0"), true, ar, s0);
@@ -1124,7 +1380,7 @@ void Engine::refine_lane(int B, const int32_t* pos, float* out, cudaStream_t st)
   F32T d = alloc_f32(ar, B, 15, 15, 32);
   {
     Scope sc(this, "deconv", "refine_misc", 2.0 * B * 256 * 7200, 4.0 * (256.0 * 7200 + B * 7200.0), st);
-    launch_gather_corr(corr, pos, p3, st); ++launches_;
+    launch_gather_corr(corr, pos, p3, std::ldexp(1.f, -corr.sexp), st); ++launches_;
     launch_deconv(p3, deconv_w_, deconv_b_, d.p, B, 256, 7200, 32, st); ++launches_;
   }
   F32T h2a = small(d, nullptr, 15, L(R + "h2.0"), true, nullptr, ar, st);
@@ -1353,7 +1609,7 @@ void Engine::do_export(const char* what, float* out, int64_t* shape4, cudaStream
   if (std::string(what) == "zf") {
     SMK_CHECK(have_zf_, "no cached tensor named 'zf'");
     if (shape4 != nullptr) { shape4[0] = zf_.B; shape4[1] = zf_.C; shape4[2] = zf_.H; shape4[3] = zf_.W; }
-    if (out != nullptr) { launch_split_to_f32(zf_, out, st); ++launches_; }
+    if (out != nullptr) { launch_split_to_f32(zf_, out, st, std::ldexp(1.f, -zf_.sexp)); ++launches_; }
     return;
   }
   int total_B = 0;
@@ -1362,7 +1618,10 @@ void Engine::do_export(const char* what, float* out, int64_t* shape4, cudaStream
     SMK_CHECK(it != lanes_[l].named.end(), std::string("no cached tensor named '") + what + "'");
     const Act& a = it->second;
     if (shape4 != nullptr) { shape4[1] = a.C; shape4[2] = a.H; shape4[3] = a.W; }
-    if (out != nullptr) { launch_split_to_f32(a, out + (size_t)total_B * a.C * a.H * a.W, st); ++launches_; }
+    if (out != nullptr) {
+      launch_split_to_f32(a, out + (size_t)total_B * a.C * a.H * a.W, st, std::ldexp(1.f, -a.sexp));
+      ++launches_;
+    }
     total_B += a.B;
   }
   if (shape4 != nullptr) shape4[0] = total_B;
@@ -1540,6 +1799,20 @@ int sm_engine_adopt_weights(sm_engine* e) {
   SM_API_BEGIN
   SMK_CHECK(e, "null argument");
   e->impl->adopt_weights();
+  SM_API_END
+}
+
+int sm_engine_calibrate(sm_engine* e, int32_t B, const float* z_nchw, const float* x_nchw, void* stream) {
+  SM_API_BEGIN
+  SMK_CHECK(e && z_nchw && x_nchw, "null argument");
+  e->impl->calibrate(B, z_nchw, x_nchw, static_cast<cudaStream_t>(stream));
+  SM_API_END
+}
+
+int sm_engine_status(sm_engine* e, int32_t* flags) {
+  SM_API_BEGIN
+  SMK_CHECK(e && flags, "null argument");
+  *flags = e->impl->status();
   SM_API_END
 }
 

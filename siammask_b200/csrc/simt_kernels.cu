@@ -188,20 +188,29 @@ __global__ void maxpool_kernel(Act in, Act out) {
 // fp32 in shared memory once (each element is read from L2 exactly once), then every thread (channel, output
 // row) slides a KHxKW window along the row out of smem.  Lanes are consecutive channels: conflict-free LDS and
 // contiguous 64-byte stores per plane.
-template <int KH, int KW, int XC_CH>
-__global__ void __launch_bounds__(256) xcorr_nhwc_kernel(Act x, const __half* __restrict__ k_hi,
-                                                         const __half* __restrict__ k_lo, Act out) {
-  extern __shared__ float xs[];                  // [H*W][XC_CH]
+// Register-blocked variant (same mapping idea as xcorr_bulk_sm100.cu): lane = channel (32 consecutive channels of one
+// stream: every shared-memory access of a warp is one conflict-free 128-byte row), and a thread owns a
+// (row block x column strip) task of NR x SW outputs: per input row SW+KW-1 loads feed NR..KH*SW*KW FMAs.  The tile
+// is reconstructed to fp32 in shared memory once; 2 blocks per SM so one block's load phase overlaps the other's math.
+template <int KH, int KW, int NR, int SW, int NTHREADS>
+__global__ void __launch_bounds__(NTHREADS, 2) xcorr_nhwc_kernel(Act x, const __half* __restrict__ k_hi,
+                                                                  const __half* __restrict__ k_lo, Act out,
+                                                                  int band_rows, float mul, int* __restrict__ ovf) {
+  constexpr int XC_CH = 32;
+  extern __shared__ float xs[];                  // [(band rows + KH - 1) * W][32]
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * XC_CH;
+  const int y0 = blockIdx.z * band_rows;                             // first output row of this block's band
+  const int Hob = min(band_rows, out.H - y0);                        // output rows of the band
   const __half* __restrict__ xh = x.hi;
   const __half* __restrict__ xl = x.lo;
-  const int npix = x.H * x.W;
+  const int npix = (Hob + KH - 1) * x.W;
+  const size_t pix0 = (size_t)b * x.H * x.W + (size_t)y0 * x.W;
   // cooperative load: 8 channels (16 B per plane) per thread-iteration
-  for (int idx = threadIdx.x; idx < npix * (XC_CH / 8); idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < npix * (XC_CH / 8); idx += NTHREADS) {
     const int pix = idx / (XC_CH / 8);
     const int cc = (idx - pix * (XC_CH / 8)) * 8;
-    const size_t src = ((size_t)b * npix + pix) * x.C + c0 + cc;
+    const size_t src = (pix0 + pix) * x.C + c0 + cc;
     const uint4 h = *reinterpret_cast<const uint4*>(xh + src);
     const __half2* hh = reinterpret_cast<const __half2*>(&h);
     float v[8];
@@ -217,40 +226,57 @@ __global__ void __launch_bounds__(256) xcorr_nhwc_kernel(Act x, const __half* __
     dst[0] = make_float4(v[0], v[1], v[2], v[3]);
     dst[1] = make_float4(v[4], v[5], v[6], v[7]);
   }
-  const int lane_c = threadIdx.x % XC_CH;          // channel within the chunk
-  const int c = c0 + lane_c;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = c0 + lane;
   float kk[KH][KW];
 #pragma unroll
   for (int u = 0; u < KH; ++u)
 #pragma unroll
     for (int v = 0; v < KW; ++v) kk[u][v] = split_load(k_hi, k_lo, (((size_t)b * KH + u) * KW + v) * x.C + c);
   __syncthreads();
-  const int rows_per_pass = blockDim.x / XC_CH;
-  for (int i = threadIdx.x / XC_CH; i < out.H; i += rows_per_pass) {
-    float win[KH][KW];
+  const int Ho = Hob, Wo = out.W, W = x.W;
+  const int nrb = (Ho + NR - 1) / NR, nst = (Wo + SW - 1) / SW;
+  for (int task = warp; task < nrb * nst; task += NTHREADS / 32) {      // warp-uniform
+    const int rb = task / nst, stp = task - rb * nst;
+    const int r0 = rb * NR, q0 = stp * SW;
+    const int nr = min(NR, Ho - r0), nc = min(SW, Wo - q0);
+    float acc[NR][SW];
 #pragma unroll
-    for (int u = 0; u < KH; ++u)
+    for (int i = 0; i < NR; ++i)
 #pragma unroll
-      for (int v = 0; v < KW - 1; ++v) win[u][v + 1] = xs[((size_t)(i + u) * x.W + v) * XC_CH + lane_c];
-    for (int j = 0; j < out.W; ++j) {
+      for (int q = 0; q < SW; ++q) acc[i][q] = 0.f;
+    const float* row = xs + ((size_t)r0 * W + q0) * XC_CH + lane;
 #pragma unroll
-      for (int u = 0; u < KH; ++u) {
+    for (int r = 0; r < NR + KH - 1; ++r) {
+      if (r < nr + KH - 1) {
+        float xr[SW + KW - 1];
 #pragma unroll
-        for (int v = 0; v < KW - 1; ++v) win[u][v] = win[u][v + 1];
-        win[u][KW - 1] = xs[((size_t)(i + u) * x.W + j + KW - 1) * XC_CH + lane_c];
+        for (int q = 0; q < SW + KW - 1; ++q) xr[q] = q < nc + KW - 1 ? row[(r * W + q) * XC_CH] : 0.f;
+#pragma unroll
+        for (int u = 0; u < KH; ++u) {
+          const int i = r - u;
+          if (i >= 0 && i < NR && i < nr) {
+#pragma unroll
+            for (int q = 0; q < SW; ++q)
+#pragma unroll
+              for (int v = 0; v < KW; ++v) acc[i][q] = fmaf(xr[q + v], kk[u][v], acc[i][q]);
+          }
+        }
       }
-      float part[KH];                      // one partial sum per kernel row: KH independent FMA chains
-#pragma unroll
-      for (int u = 0; u < KH; ++u) {
-        part[u] = win[u][0] * kk[u][0];
-#pragma unroll
-        for (int v = 1; v < KW; ++v) part[u] = fmaf(win[u][v], kk[u][v], part[u]);
-      }
-      float acc = part[0];
-#pragma unroll
-      for (int u = 1; u < KH; ++u) acc += part[u];
-      split_store(out.hi, out.lo, (((size_t)b * out.H + i) * out.W + j) * out.C + c, acc);
     }
+    float amax = 0.f;
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+      if (i < nr) {
+#pragma unroll
+        for (int q = 0; q < SW; ++q)
+          if (q < nc) {
+            const float v = acc[i][q] * mul;        // mul = 2^(s_corr - s_search - s_kernel): static activation scales
+            amax = fmaxf(amax, fabsf(v));
+            split_store(out.hi, out.lo, (((size_t)b * out.H + y0 + r0 + i) * Wo + q0 + q) * out.C + c, v);
+          }
+      }
+    flag_if_out_of_range(amax, ovf);
   }
 }
 
@@ -358,11 +384,12 @@ __global__ void crop_kernel(Act in, Act out, const int32_t* __restrict__ pos, in
 }
 
 // p3 = corr_feature[b, :, dy, dx] (custom.py:144-145) as fp32 [B][C]
-__global__ void gather_corr_kernel(Act corr, const int32_t* __restrict__ pos, float* __restrict__ out) {
+__global__ void gather_corr_kernel(Act corr, const int32_t* __restrict__ pos, float* __restrict__ out, float mul) {
   const int b = blockIdx.x;
   const int dy = min(max(pos[2 * b], 0), corr.H - 1), dx = min(max(pos[2 * b + 1], 0), corr.W - 1);
   for (int c = threadIdx.x; c < corr.C; c += blockDim.x)
-    out[(size_t)b * corr.C + c] = split_load(corr.hi, corr.lo, (((size_t)b * corr.H + dy) * corr.W + dx) * corr.C + c);
+    out[(size_t)b * corr.C + c] =
+        mul * split_load(corr.hi, corr.lo, (((size_t)b * corr.H + dy) * corr.W + dx) * corr.C + c);
 }
 
 // mask[b, :, dy, dx] of the raw 63*63-channel mask head output (tools/test.py:259-260, the non-refine branch)
@@ -403,6 +430,31 @@ __global__ void __launch_bounds__(256) deconv_kernel(const float* __restrict__ p
     if (b0 + t < B) out[(size_t)(b0 + t) * N + n] = acc[t] + bv;
 }
 
+// max |hi| of a split-plane activation (calibration of the static activation scales): float bits are monotone for
+// non-negative values, so an integer atomicMax on the bits of |v| works; inf / NaN propagate as large bit patterns.
+__global__ void absmax_kernel(const __half* __restrict__ hi, size_t n8, float* __restrict__ slot) {
+  float m = 0.f;
+  unsigned bad = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(hi)[i];
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = __half22float2(h[t]);
+      if (!(fabsf(f.x) <= 65504.f) || !(fabsf(f.y) <= 65504.f)) bad = 1;
+      m = fmaxf(m, fmaxf(fabsf(f.x), fabsf(f.y)));
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (bad) m = INFINITY;
+    atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(m));
+  }
+}
+
 // NCHW fp32 -> NHWC split planes (standalone-operator entry, sm_conv2d).
 __global__ void import_nchw_kernel(const float* __restrict__ x, Act out) {
   const size_t total = out.numel();
@@ -416,14 +468,14 @@ __global__ void import_nchw_kernel(const float* __restrict__ x, Act out) {
 }
 
 // NHWC split planes -> NCHW fp32 (exports cached features for parity checks / the Python boundary).
-__global__ void export_nchw_kernel(Act in, float* __restrict__ out) {
+__global__ void export_nchw_kernel(Act in, float* __restrict__ out, float mul) {
   const size_t total = in.numel();
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int w = idx % in.W;
     const int h = (idx / in.W) % in.H;
     const int c = (idx / ((size_t)in.W * in.H)) % in.C;
     const int b = idx / ((size_t)in.W * in.H * in.C);
-    out[idx] = split_load(in.hi, in.lo, (((size_t)b * in.H + h) * in.W + w) * in.C + c);
+    out[idx] = mul * split_load(in.hi, in.lo, (((size_t)b * in.H + h) * in.W + w) * in.C + c);
   }
 }
 
@@ -925,23 +977,21 @@ void launch_maxpool3s2(const Act& in, Act out, cudaStream_t st) {
   SMK_CUDA(cudaGetLastError());
 }
 
-void launch_xcorr_nhwc(const Act& x, const __half* k_hi, const __half* k_lo, int kh, int kw, Act out, cudaStream_t st) {
+void launch_xcorr_nhwc(const Act& x, const __half* k_hi, const __half* k_lo, int kh, int kw, Act out, float mul, int* ovf,
+                       cudaStream_t st) {
   SMK_CHECK(kh == 5 && kw == 5, "engine xcorr is specialised for the 5x5 template kernel");
-  SMK_CHECK(out.H == x.H - kh + 1 && out.W == x.W - kw + 1 && out.C == x.C && x.C % 2 == 0, "xcorr shapes");
-  SMK_CHECK(x.C % 32 == 0, "xcorr channel chunking");
-  // 32 channels per block when the HxW tile fits (29x29 @255: 105 KB), else 16 (45x45 @383: 127 KB)
-  const size_t smem32 = (size_t)x.H * x.W * 32 * sizeof(float);
-  if (smem32 <= 110 * 1024) {
-    static unsigned long long attr = 0;
-    ensure_dynamic_smem(xcorr_nhwc_kernel<5, 5, 32>, 110 * 1024, attr);
-    xcorr_nhwc_kernel<5, 5, 32><<<dim3(x.C / 32, x.B), 256, smem32, st>>>(x, k_hi, k_lo, out);
-  } else {
-    const size_t smem16 = smem32 / 2;
-    SMK_CHECK(smem16 <= 220 * 1024, "xcorr input tile does not fit shared memory");
-    static unsigned long long attr = 0;
-    ensure_dynamic_smem(xcorr_nhwc_kernel<5, 5, 16>, 220 * 1024, attr);
-    xcorr_nhwc_kernel<5, 5, 16><<<dim3(x.C / 16, x.B), 256, smem16, st>>>(x, k_hi, k_lo, out);
-  }
+  SMK_CHECK(out.H == x.H - kh + 1 && out.W == x.W - kw + 1 && out.C == x.C && x.C % 32 == 0, "xcorr shapes");
+  // one block = one stream x 32 channels x a band of output rows, its input rows reconstructed to fp32 in smem:
+  // 29x29 @255 is one band (105 KB, 2 blocks per SM); 45x45 @383 takes two bands of 21 / 20 rows (144 KB)
+  const int Ho = out.H;
+  int bands = 1;
+  while ((size_t)((Ho + bands - 1) / bands + kh - 1) * x.W * 32 * sizeof(float) > 160 * 1024) ++bands;
+  const int band_rows = (Ho + bands - 1) / bands;
+  const size_t smem = (size_t)(band_rows + kh - 1) * x.W * 32 * sizeof(float);
+  auto kern = xcorr_nhwc_kernel<5, 5, 7, 5, 320>;
+  static unsigned long long attr = 0;
+  ensure_dynamic_smem(kern, 160 * 1024, attr);
+  kern<<<dim3(x.C / 32, x.B, bands), 320, smem, st>>>(x, k_hi, k_lo, out, band_rows, mul, ovf);
   SMK_CUDA(cudaGetLastError());
 }
 
@@ -981,8 +1031,8 @@ void launch_refine_crop(const Act& in, const int32_t* pos, int pos_max, int scal
   SMK_CUDA(cudaGetLastError());
 }
 
-void launch_gather_corr(const Act& corr, const int32_t* pos, float* out, cudaStream_t st) {
-  gather_corr_kernel<<<corr.B, 256, 0, st>>>(corr, pos, out);
+void launch_gather_corr(const Act& corr, const int32_t* pos, float* out, float mul, cudaStream_t st) {
+  gather_corr_kernel<<<corr.B, 256, 0, st>>>(corr, pos, out, mul);
   SMK_CUDA(cudaGetLastError());
 }
 
@@ -998,8 +1048,14 @@ void launch_deconv(const float* p3, const float* w, const float* bias, float* ou
   SMK_CUDA(cudaGetLastError());
 }
 
-void launch_split_to_f32(const Act& in, float* out, cudaStream_t st) {
-  export_nchw_kernel<<<grid_for(in.numel(), 256), 256, 0, st>>>(in, out);
+void launch_absmax(const Act& a, float* slot, cudaStream_t st) {
+  SMK_CHECK(a.numel() % 8 == 0, "absmax: element count");
+  absmax_kernel<<<grid_for(a.numel() / 8, 256), 256, 0, st>>>(a.hi, a.numel() / 8, slot);
+  SMK_CUDA(cudaGetLastError());
+}
+
+void launch_split_to_f32(const Act& in, float* out, cudaStream_t st, float mul) {
+  export_nchw_kernel<<<grid_for(in.numel(), 256), 256, 0, st>>>(in, out, mul);
   SMK_CUDA(cudaGetLastError());
 }
 

@@ -35,6 +35,7 @@ struct StemParams {
   const float* x;         // [B][3][S][S]
   const float* alpha;     // [64] 2^-e
   const float* beta;      // [64]
+  int* ovf;               // overflow flag (values outside fp16's range), may be null
   int B, S, So, M, m_tiles;
 };
 
@@ -227,6 +228,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) stem_tc_kernel(const __grid_const
         v[j + 2] = fmaxf(fmaf(__uint_as_float(r[j + 2]), al.z, be.z), 0.f);
         v[j + 3] = fmaxf(fmaf(__uint_as_float(r[j + 3]), al.w, be.w), 0.f);
       }
+      {
+        float amax = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) amax = fmaxf(amax, v[j]);
+        flag_if_out_of_range(amax, p.ovf);
+      }
       if (leader) tma_store_wait_read<0>();
       __syncwarp();
 #pragma unroll
@@ -270,10 +277,11 @@ CUtensorMap make_map_2d_any(const __half* base, uint64_t inner, uint64_t outer, 
                             int swizzle_bytes);
 
 void launch_stem_tc(const float* x, int B, int S, const __half* w_hi, const __half* w_lo, const float* alpha,
-                    const float* beta, Act out, int num_sms, cudaStream_t st) {
+                    const float* beta, Act out, int num_sms, cudaStream_t st, int* ovf) {
   const int So = (S - 7) / 2 + 1;
   SMK_CHECK(out.H == So && out.W == So && out.C == 64 && out.B == B, "stem output shape");
   StemParams p;
+  p.ovf = ovf;
   p.x = x;
   p.alpha = alpha;
   p.beta = beta;

@@ -148,6 +148,26 @@ class Custom:
     def adopt_weights(self):
         _lib.check(self._lib.sm_engine_adopt_weights(self._engine))
 
+    @torch.no_grad()
+    def calibrate(self, z, x):
+        """Pick static power-of-two activation scales from a representative sample (z [B,3,127,127], x [B,3,S,S], raw
+        0..255 crops; engine slots 0..B-1 are overwritten).  Results are unchanged for well-scaled checkpoints; it
+        is what keeps checkpoints whose activations sit far from O(1) inside the fp16 split format's range."""
+        z, x = self._prep(z, 127), self._prep(x, self.search_size)
+        if z.shape[0] != x.shape[0]:
+            raise ValueError("paired sample batch expected")
+        with torch.cuda.device(self._device):
+            self._fence_in()
+            _lib.check(self._lib.sm_engine_calibrate(self._engine, z.shape[0], z.data_ptr(), x.data_ptr(), self._stream()))
+            self._fence_out()
+        return self
+
+    def status(self) -> int:
+        """Synchronises; bit 0 set = an activation left fp16's range (call `calibrate`)."""
+        v = C.c_int32()
+        _lib.check(self._lib.sm_engine_status(self._engine, C.byref(v)))
+        return int(v.value)
+
     # packed-weight file (SURVEY §8f row 4): BN-folded, repacked, fp16-split arena exactly as it sits in HBM, so a
     # fleet of ranks loads (or receives by broadcast) the blob instead of re-folding the 21 M-parameter checkpoint
     _PACK_MAGIC = b"SMB200PK1"
