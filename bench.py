@@ -555,6 +555,8 @@ def run_gpu(args, rank, local_rank, world):
         "parity_check": parity,
         "device_bytes": m.device_bytes,
     }
+    if world == 1 and sharp and S == 255 and not args.no_loop:
+        result["loop"] = tracker_loop_rate(args, m, B, dev)
     if world == 1 and not args.no_cpu:
         cfps, cores, sample, _ = run_cpu_fleet(args, seconds=args.cpu_seconds)
         result["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores, "host_cpus": os.cpu_count(),
@@ -566,6 +568,35 @@ def run_gpu(args, rank, local_rank, world):
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
+
+
+def tracker_loop_rate(args, m, B, dev, seconds=1.5):
+    """The whole tracker loop of tools/test.py:172-315 for B concurrent streams with device-resident state
+    (siammask_b200.tracker.BatchTracker): uint8 frames in HBM -> search-window arithmetic -> cv2-exact crop + resize ->
+    track_mask + selection + refine -> state update -> mask paste-back + threshold.  Frames: synthetic 480x640 BGR,
+    one per stream, already on the device (a video decoder's output)."""
+    import torch
+    from siammask_b200.tracker import BatchTracker, TrackerParams
+    H, W = 480, 640
+    g = torch.Generator(device=dev).manual_seed(7)
+    frames = [(torch.rand(B, H, W, 3, device=dev, generator=g) * 255).to(torch.uint8) for _ in range(2)]
+    boxes = np.tile(np.array([[280.0, 200.0, 80.0, 60.0]]), (B, 1)) + np.random.RandomState(0).rand(B, 4) * 20
+    bt = BatchTracker(m, TrackerParams(instance_size=args.search), slot0=0)
+    bt.init(frames[0], boxes)
+    for i in range(3):
+        bt.track(frames[i % 2])
+    torch.cuda.synchronize(dev)
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        r = bt.track(frames[n % 2])
+        n += 1
+        if n % 4 == 0:
+            r.state[0, 0].item()                 # the host looks at results now and then (bounded queue depth)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    return {"value": B * n / dt, "unit": "frames/s", "frames": n * B, "seconds": dt, "frame_hw": [H, W],
+            "what": "BatchTracker.track(mask=True, refine=True): sm_tracker_prepare + sm_crop_resize + sm_step + "
+                    "sm_tracker_update + sm_warp_affine + threshold, uint8 frames resident in HBM, masks left on the device"}
 
 
 def verify_against_oracle(args, m, sd, z, x, anchors_dev, window_dev, tsz_dev, B, dev, sharp):
@@ -634,6 +665,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="length of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-context", action="store_true", help="skip the PyTorch/cuDNN context leg")
+    ap.add_argument("--no-loop", action="store_true", help="skip the whole-tracker-loop leg")
     ap.add_argument("--no-verify", dest="verify", action="store_false", help="skip the oracle parity check")
     ap.add_argument("--traffic-file", default="r02_traffic.json")
     ap.add_argument("--dump-layers", default=None, help="write the per-launch CUDA-event table of one step here")

@@ -146,8 +146,8 @@ void launch_ref_conv(const Act& in, const ConvGeom& g, const float* w_krsc_cout,
 void launch_stem(const float* x_nchw, int B, int S, const float* w, const float* alpha, const float* beta, Act out,
                  cudaStream_t st);
 void launch_maxpool3s2(const Act& in, Act out, cudaStream_t st);
-void launch_xcorr_nhwc(const Act& x, const __half* k_hi, const __half* k_lo, int kh, int kw, Act out, float mul,
-                       int* ovf, cudaStream_t st);
+void launch_xcorr_nhwc(const Act& x, int c_off, const __half* k_hi, const __half* k_lo, int kh, int kw, Act out,
+                       float mul, int* ovf, cudaStream_t st);
 void launch_absmax(const Act& a, float* slot, cudaStream_t st);
 void launch_xcorr_nchw_f32(const float* x, const float* k, float* out, int planes, int H, int W, int kh, int kw,
                            cudaStream_t st);

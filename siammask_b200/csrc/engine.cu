@@ -52,9 +52,12 @@ struct ConvW {
   // alpha and beta in the arena are packed for exactly these values (quantize_layer).
   int s_in = 0, s_in2 = 0, s_res = 0, s_out = 0;
   bool f32_out = false;               // output leaves as fp32 (heads, refine inputs): s_out stays 0
+  std::vector<std::string> cat_keys;  // non-empty: Cout-concatenation of these layers (one GEMM for all conv_search branches)
   std::string src_in, src_in2, src_res;   // producer tensor names, recorded by the calibration pass
   std::vector<double> shift, shift2;      // unscaled folded shifts (host), kept so the layer can be re-quantized
 };
+
+constexpr const char* kSearchCat = "heads.conv_search_cat";
 
 struct F32T {                         // fp32 NHWC tensor (refine stage)
   float* p = nullptr;
@@ -467,6 +470,12 @@ void Engine::build_layer_table() {
     add_layer(h.first + "head.0", h.first + "head.1", {256, 256, 1, 1, 1, 0, 1});
     add_layer(h.first + "head.3", "", {256, h.second, 1, 1, 1, 0, 1});
   }
+  {
+    // DepthCorr.conv_search of every branch reads the same search feature (models/rpn.py:63-67): one GEMM with the
+    // branches' output channels concatenated (N = 256 x branches) instead of one launch and one pass over xf per branch
+    ConvW& cat = add_layer(kSearchCat, "", {256, 256 * n_branches_, 3, 3, 1, 0, 1});
+    for (auto& h : heads) cat.cat_keys.push_back(h.first + "conv_search.0");
+  }
   if (cfg_.with_mask) {
     const std::string R = "refine_model.";
     auto c3 = [&](const std::string& k, int ci, int co) { add_layer(R + k, "", {ci, co, 3, 3, 1, 1, 1}); };
@@ -666,8 +675,8 @@ size_t Engine::measure_arena(int B, int S, bool search) {
   Act xf = backbone(nullptr, B, S, ar, search, nullptr);
   if (search) {
     // heads: conv_search, corr, head.0 per branch
+    alloc_act(ar, B, xf.H - 2, xf.W - 2, 256 * n_branches_);      // conv_search of all branches (one GEMM or one each)
     for (int br = 0; br < n_branches_; ++br) {
-      alloc_act(ar, B, xf.H - 2, xf.W - 2, 256);
       alloc_act(ar, B, R_, R_, 256);
       alloc_act(ar, B, R_, R_, 256);
     }
@@ -720,6 +729,21 @@ void fold_affine(const std::map<std::string, const sm_tensor_desc*>& sd, const s
 void Engine::fold_layer(ConvW& L, const std::map<std::string, const sm_tensor_desc*>& sd, uint8_t* host) {
   const ConvGeom& g = L.g;
   const size_t K = (size_t)g.KH * g.KW * g.Cin;
+  if (!L.cat_keys.empty()) {          // concatenation of already folded layers along Cout
+    float* w_cat = reinterpret_cast<float*>(host + L.off_wref);
+    L.shift.assign(g.Cout, 0.0);
+    int n0 = 0;
+    for (const auto& key : L.cat_keys) {
+      const ConvW& src = layers_.at(key);
+      SMK_CHECK(src.g.Cin == g.Cin && src.g.KH == g.KH && !src.shift.empty(), "concatenated layers must share their geometry");
+      const float* ws = reinterpret_cast<const float*>(host + src.off_wref);
+      for (size_t k = 0; k < K; ++k)
+        for (int n = 0; n < src.g.Cout; ++n) w_cat[k * g.Cout + n0 + n] = ws[k * src.g.Cout + n];
+      for (int n = 0; n < src.g.Cout; ++n) L.shift[n0 + n] = src.shift[n];
+      n0 += src.g.Cout;
+    }
+    return;
+  }
   const float* w = find_tensor(sd, L.conv_key + ".weight", K * g.Cout);   // OIHW
   std::vector<double> scale;
   fold_affine(sd, L.conv_key, L.bn_key, g.Cout, scale, L.shift);
@@ -926,6 +950,16 @@ void Engine::calibrate(int B, const float* z, const float* x, cudaStream_t st) {
     else tscale_[name] = v;
   };
   auto rewire_and_upload = [&]() {
+    {
+      // the per-branch conv_search layers (used when only some branches run) mirror the concatenated one
+      const ConvW& cat = layers_.at(kSearchCat);
+      if (!cat.src_in.empty())
+        for (const auto& k : cat.cat_keys) {
+          ConvW& w = layers_.at(k);
+          w.src_in = cat.src_in;
+          w.s_out = cat.s_out;
+        }
+    }
     for (auto& kv : layers_) {
       ConvW& w = kv.second;
       if (!w.src_in.empty()) w.s_in = scale_of(w.src_in);
@@ -1252,21 +1286,26 @@ void Engine::track_lane(int slot0, int B, const float* x, float* cls, float* loc
   cur_->named["search"] = xf;
   const int nb = (want_feats || want_mask_head) ? 3 : 2;
   float* outs[3] = {cls, loc, mask};
+  // all branches wanted: their conv_search layers run as ONE GEMM over xf (N = 256 x branches)
+  static const bool no_cat = std::getenv("SMB200_NO_SEARCH_CAT") != nullptr;
+  const bool use_cat = nb == n_branches_ && cfg_.backend == SM_BACKEND_TENSOR && !no_cat;
+  Act cs_all;
+  if (use_cat) cs_all = conv(xf, L(kSearchCat), true, nullptr, search_arena, st);
   for (int br = 0; br < nb; ++br) {
     // the branches only share their input: run them side by side (their 1x1 heads and the xcorr do not fill
     // the GPU on their own)
     cudaStream_t bs = (concurrent() && br > 0) ? cur_->aux[br - 1] : st;
     order_after(st, bs);
     const std::string P = kBranch[br];
-    Act cs = conv(xf, L(P + "conv_search.0"), true, nullptr, search_arena, bs);
+    Act cs = use_cat ? cs_all : conv(xf, L(P + "conv_search.0"), true, nullptr, search_arena, bs);
     Act corr = alloc_act(search_arena, B, cs.H - 4, cs.W - 4, 256);
     const size_t off = ((size_t)br * cfg_.num_slots + slot0) * 25 * 256;
     {
       Scope sc(this, std::string(kCorrName[br]), "xcorr", 2.0 * 25 * corr.numel(),
-               4.0 * (cs.numel() + corr.numel() + (double)B * 25 * 256), bs);
+               4.0 * (2.0 * corr.numel() + (double)B * cs.H * cs.W * 256 + (double)B * 25 * 256), bs);
       corr.sexp = tscale(kCorrName[br]);
       const int s_kc = L(P + "conv_kernel.0").s_out;
-      launch_xcorr_nhwc(cs, kcache_hi_ + off, exact_ ? kcache_lo_ + off : nullptr, 5, 5, corr,
+      launch_xcorr_nhwc(cs, use_cat ? 256 * br : 0, kcache_hi_ + off, exact_ ? kcache_lo_ + off : nullptr, 5, 5, corr,
                         std::ldexp(1.f, corr.sexp - cs.sexp - s_kc), ovf_flag_, bs);
       ++launches_;
       last_end_[corr.hi] = +1;

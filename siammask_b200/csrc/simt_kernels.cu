@@ -195,7 +195,8 @@ __global__ void maxpool_kernel(Act in, Act out) {
 template <int KH, int KW, int NR, int SW, int NTHREADS>
 __global__ void __launch_bounds__(NTHREADS, 2) xcorr_nhwc_kernel(Act x, const __half* __restrict__ k_hi,
                                                                   const __half* __restrict__ k_lo, Act out,
-                                                                  int band_rows, float mul, int* __restrict__ ovf) {
+                                                                  int band_rows, int c_off, float mul,
+                                                                  int* __restrict__ ovf) {
   constexpr int XC_CH = 32;
   extern __shared__ float xs[];                  // [(band rows + KH - 1) * W][32]
   const int b = blockIdx.y;
@@ -206,25 +207,44 @@ __global__ void __launch_bounds__(NTHREADS, 2) xcorr_nhwc_kernel(Act x, const __
   const __half* __restrict__ xl = x.lo;
   const int npix = (Hob + KH - 1) * x.W;
   const size_t pix0 = (size_t)b * x.H * x.W + (size_t)y0 * x.W;
-  // cooperative load: 8 channels (16 B per plane) per thread-iteration
-  for (int idx = threadIdx.x; idx < npix * (XC_CH / 8); idx += NTHREADS) {
-    const int pix = idx / (XC_CH / 8);
-    const int cc = (idx - pix * (XC_CH / 8)) * 8;
-    const size_t src = (pix0 + pix) * x.C + c0 + cc;
-    const uint4 h = *reinterpret_cast<const uint4*>(xh + src);
-    const __half2* hh = reinterpret_cast<const __half2*>(&h);
-    float v[8];
+  // cooperative load: 8 channels (16 B per plane) per item; LD_U items per thread are fetched before any of them is
+  // converted, so each thread keeps 2 * LD_U independent 16-byte loads in flight (the tile comes from L2 / HBM:
+  // with one item at a time the load phase was latency-bound and dominated the kernel)
+  constexpr int LD_U = 4;
+  const int nitems = npix * (XC_CH / 8);
+  for (int base = threadIdx.x; base < nitems; base += NTHREADS * LD_U) {
+    uint4 hbuf[LD_U], lbuf[LD_U];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) { const float2 f = __half22float2(hh[t]); v[2 * t] = f.x; v[2 * t + 1] = f.y; }
-    if (xl != nullptr) {
-      const uint4 l = *reinterpret_cast<const uint4*>(xl + src);
-      const __half2* ll = reinterpret_cast<const __half2*>(&l);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) { const float2 f = __half22float2(ll[t]); v[2 * t] += f.x; v[2 * t + 1] += f.y; }
+    for (int t = 0; t < LD_U; ++t) {
+      const int idx = base + t * NTHREADS;
+      if (idx < nitems) {
+        const int pix = idx / (XC_CH / 8);
+        const int cc = (idx - pix * (XC_CH / 8)) * 8;
+        const size_t src = (pix0 + pix) * x.C + c_off + c0 + cc;   // c_off: this branch's slice of a concatenated search conv
+        hbuf[t] = *reinterpret_cast<const uint4*>(xh + src);
+        lbuf[t] = xl != nullptr ? *reinterpret_cast<const uint4*>(xl + src) : make_uint4(0, 0, 0, 0);
+      }
     }
-    float4* dst = reinterpret_cast<float4*>(xs + (size_t)pix * XC_CH + cc);
-    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+    for (int t = 0; t < LD_U; ++t) {
+      const int idx = base + t * NTHREADS;
+      if (idx < nitems) {
+        const int pix = idx / (XC_CH / 8);
+        const int cc = (idx - pix * (XC_CH / 8)) * 8;
+        const __half2* hh = reinterpret_cast<const __half2*>(&hbuf[t]);
+        const __half2* ll = reinterpret_cast<const __half2*>(&lbuf[t]);
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __half22float2(hh[q]), g = __half22float2(ll[q]);
+          v[2 * q] = f.x + g.x;
+          v[2 * q + 1] = f.y + g.y;
+        }
+        float4* dst = reinterpret_cast<float4*>(xs + (size_t)pix * XC_CH + cc);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = c0 + lane;
@@ -232,7 +252,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) xcorr_nhwc_kernel(Act x, const __
 #pragma unroll
   for (int u = 0; u < KH; ++u)
 #pragma unroll
-    for (int v = 0; v < KW; ++v) kk[u][v] = split_load(k_hi, k_lo, (((size_t)b * KH + u) * KW + v) * x.C + c);
+    for (int v = 0; v < KW; ++v) kk[u][v] = split_load(k_hi, k_lo, (((size_t)b * KH + u) * KW + v) * out.C + c);
   __syncthreads();
   const int Ho = Hob, Wo = out.W, W = x.W;
   const int nrb = (Ho + NR - 1) / NR, nst = (Wo + SW - 1) / SW;
@@ -977,10 +997,11 @@ void launch_maxpool3s2(const Act& in, Act out, cudaStream_t st) {
   SMK_CUDA(cudaGetLastError());
 }
 
-void launch_xcorr_nhwc(const Act& x, const __half* k_hi, const __half* k_lo, int kh, int kw, Act out, float mul, int* ovf,
-                       cudaStream_t st) {
+void launch_xcorr_nhwc(const Act& x, int c_off, const __half* k_hi, const __half* k_lo, int kh, int kw, Act out, float mul,
+                       int* ovf, cudaStream_t st) {
   SMK_CHECK(kh == 5 && kw == 5, "engine xcorr is specialised for the 5x5 template kernel");
-  SMK_CHECK(out.H == x.H - kh + 1 && out.W == x.W - kw + 1 && out.C == x.C && x.C % 32 == 0, "xcorr shapes");
+  SMK_CHECK(out.H == x.H - kh + 1 && out.W == x.W - kw + 1 && c_off % 8 == 0 && c_off + out.C <= x.C && out.C % 32 == 0,
+            "xcorr shapes");
   // one block = one stream x 32 channels x a band of output rows, its input rows reconstructed to fp32 in smem:
   // 29x29 @255 is one band (105 KB, 2 blocks per SM); 45x45 @383 takes two bands of 21 / 20 rows (144 KB)
   const int Ho = out.H;
@@ -991,7 +1012,7 @@ void launch_xcorr_nhwc(const Act& x, const __half* k_hi, const __half* k_lo, int
   auto kern = xcorr_nhwc_kernel<5, 5, 7, 5, 320>;
   static unsigned long long attr = 0;
   ensure_dynamic_smem(kern, 160 * 1024, attr);
-  kern<<<dim3(x.C / 32, x.B, bands), 320, smem, st>>>(x, k_hi, k_lo, out, band_rows, mul, ovf);
+  kern<<<dim3(out.C / 32, x.B, bands), 320, smem, st>>>(x, k_hi, k_lo, out, band_rows, c_off, mul, ovf);
   SMK_CUDA(cudaGetLastError());
 }
 
