@@ -812,8 +812,13 @@ void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, i
   // ... and only when the 128 x 128 tiling would fill the machine anyway: small batches (B=1: 64 tiles) are latency
   // bound and want as many CTAs as they can get
   const long long narrow_tiles = (long long)((p.M + BLOCK_M - 1) / BLOCK_M) * (cout_pad / 128);
-  const bool wide_exact = nsplit == 2 && cout_pad >= 256 && ep.out_mode == OUT_NHWC_SPLIT &&
-                          (n256 == 3 || (n256 == 1 && total_kb >= wide_kb && narrow_tiles >= num_sms));
+  // NCHW fp32 outputs (the 3969-channel mask head: K = 256, 128 x 128 tiles re-stream 64 KB of operands per k-block
+  // and sit at the L2 -> SM fabric limit): SMB200_NCHW_WIDE=1 lets them take the 256-wide (pair) tile as well
+  static const int nchw_wide = [] { const char* e = getenv("SMB200_NCHW_WIDE"); return e ? atoi(e) : 0; }();
+  const bool wide_nchw = nchw_wide != 0 && nsplit == 2 && cout_pad >= 1024 && ep.out_mode == OUT_NCHW_F32 &&
+                         narrow_tiles >= num_sms;
+  const bool wide_exact = (nsplit == 2 && cout_pad >= 256 && ep.out_mode == OUT_NHWC_SPLIT &&
+                           (n256 == 3 || (n256 == 1 && total_kb >= wide_kb && narrow_tiles >= num_sms))) || wide_nchw;
   const int block_n = cout_pad < 256 ? cout_pad : (nsplit == 2 && !wide_exact ? 128 : 256);
   const int bk = 64;
   // CTA pairs (cluster of 2, tcgen05 cta_group::2, 256 x 256 tiles): each CTA stages its own 128 A rows and half of

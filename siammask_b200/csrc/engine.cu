@@ -150,6 +150,7 @@ class Engine {
   void build_layer_table();
   void assign_blob_layout();
   size_t measure_arena(int B, int S, bool search);
+  size_t refine_arena_bytes(int B) const;
   // ---- packing
   void fold_layer(ConvW& L, const std::map<std::string, const sm_tensor_desc*>& sd, uint8_t* host);
   void quantize_layer(ConvW& L, uint8_t* host);
@@ -585,8 +586,7 @@ void Engine::construct(const sm_config& cfg) {
     ln.search.cap = measure_arena(ln.cap_B, cfg.search_size, true);
     SMK_CUDA(cudaMalloc(&ln.search.base, ln.search.cap));
     if (cfg_.with_mask) {
-      // refine stage: crops + conv outputs, ~ (61*61*64 + 31*31*(256+64) + 15*15*(512+128)) split + fp32 maps
-      ln.refine.cap = align_up((size_t)ln.cap_B * 6u * 1024 * 1024 + (1u << 20));
+      ln.refine.cap = refine_arena_bytes(ln.cap_B);
       SMK_CUDA(cudaMalloc(&ln.refine.base, ln.refine.cap));
     }
     for (int i = 0; i < kAux; ++i) SMK_CUDA(cudaStreamCreateWithFlags(&ln.aux[i], cudaStreamNonBlocking));
@@ -666,6 +666,22 @@ void Engine::release() {
   for (auto e : sync_events_) cudaEventDestroy(e);
   for (auto e : event_pool_) cudaEventDestroy(e);
   for (auto& kv : graphs_) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+}
+
+// every allocation refine_lane makes, in its order (the window sizes 15 / 31 / 61 / 127 are fixed by custom.py:131-152)
+size_t Engine::refine_arena_bytes(int B) const {
+  size_t off = 0;
+  auto add = [&](size_t bytes) { off = align_up(off) + bytes; };
+  auto act = [&](int hw, int c) { add((size_t)B * hw * hw * c * sizeof(__half)); if (exact_) add((size_t)B * hw * hw * c * sizeof(__half)); };
+  auto f32 = [&](int hw, int c) { add((size_t)B * hw * hw * c * sizeof(float)); };
+  act(15, 512); act(15, 128); f32(15, 32);          // c2, v2.0, v2.2
+  act(31, 256); act(31, 64); f32(31, 16);           // c1, v1.0, v1.2
+  act(61, 64); f32(61, 16); f32(61, 4);             // c0, v0.0, v0.2
+  add((size_t)B * 256 * sizeof(float)); f32(15, 32);// p3, deconv
+  f32(15, 32); f32(15, 32); f32(31, 16);            // h2.0, h2.2, post0
+  f32(31, 16); f32(31, 16); f32(61, 4);             // h1.0, h1.2, post1
+  f32(61, 4); f32(61, 4);                           // h0.0, h0.2 (post2 writes the caller's buffer)
+  return align_up(off + (1u << 16));
 }
 
 size_t Engine::measure_arena(int B, int S, bool search) {

@@ -1,8 +1,13 @@
+"""Small-batch latency of one whole frame (sm_step: track_mask + selection + refine), eager vs CUDA-graph replay,
+plus the host time of the call itself (enqueue only).  Used for profiles/r02_other_configs.md."""
 import sys, time, numpy as np, torch
 sys.path.insert(0, '.')
 import siammask_b200 as smb
-from siammask_b200 import tracker
+from siammask_b200 import anchors as anc
 dev = torch.device('cuda', 0)
+R = 25
+anchors_dev = torch.from_numpy(anc.generate_anchor(smb.DEFAULT_ANCHORS, R)).to(dev)
+window_dev = torch.from_numpy(anc.cosine_window(R, 5).astype(np.float32)).to(dev)
 for prec in ('exact', 'fast'):
   for B in (1, 8):
    for graphs in (False, True):
@@ -10,26 +15,21 @@ for prec in ('exact', 'fast'):
     gen = torch.Generator(device=dev).manual_seed(1)
     z = torch.rand(B, 3, 127, 127, device=dev, generator=gen) * 255
     x = torch.rand(B, 3, 255, 255, device=dev, generator=gen) * 255
-    R = 25
-    anchors_dev = torch.from_numpy(tracker.generate_anchor(smb.DEFAULT_ANCHORS, R)).to(dev)
-    window_dev = torch.from_numpy(np.tile(np.outer(np.hanning(R), np.hanning(R)).flatten(), 5).astype(np.float32)).to(dev)
-    tsz_dev = torch.rand(B, 2, device=dev, generator=gen) * 60 + 30
+    tsz = (torch.rand(B, 2, device=dev, generator=gen) * 60 + 30).double()
     m.template(z)
     def step():
-        cls, loc, _ = m.track_mask(x, mask_head=False)
-        best, sp, rec = m.select(cls, loc, anchors_dev, window_dev, tsz_dev, 0.04, 0.4)
-        return m.track_refine(sp)
+        return m.step(x, anchors_dev, window_dev, tsz, 0.04, 0.4, refine=True, mask_head=False)["refine"]
     for _ in range(5): step()
     torch.cuda.synchronize()
-    n = 50
+    n = 100
     t0 = time.perf_counter()
     for _ in range(n): step()
+    t_host = (time.perf_counter() - t0) / n          # enqueue cost (the GPU runs behind)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / n
-    # latency with a sync every frame (the tracker loop reads results on the host each frame)
     t0 = time.perf_counter()
     for _ in range(n):
-        step().cpu()
+        step().cpu()                                 # a tracker loop reads results on the host each frame
     dl = (time.perf_counter() - t0) / n
-    print(f"{prec:6s} graphs={graphs!s:5s} B={B:3d}: pipelined {1e3*dt:7.3f} ms/step = {B/dt:9.1f} FPS | synced {1e3*dl:7.3f} ms/step = {B/dl:9.1f} FPS", flush=True)
+    print(f"{prec:6s} graphs={graphs!s:5s} B={B:3d}: pipelined {1e3*dt:7.3f} ms/step = {B/dt:9.1f} FPS | synced {1e3*dl:7.3f} ms/step = {B/dl:9.1f} FPS | host enqueue {1e3*t_host:6.3f} ms", flush=True)
     del m

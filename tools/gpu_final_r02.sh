@@ -15,6 +15,10 @@ timeout 900 python bench.py --config 3 --steps 20 --warmup 3 --no-cpu --no-conte
 tail -2 gpurun_out/r02_cfg3.err; cut -c1-200 gpurun_out/r02_bench_cfg3_rpn_b256.json
 timeout 1200 python bench.py --config 5 --steps 20 --warmup 3 --no-cpu --no-context > gpurun_out/r02_bench_cfg5_s383_b128.json 2> gpurun_out/r02_cfg5.err
 tail -2 gpurun_out/r02_cfg5.err; cut -c1-200 gpurun_out/r02_bench_cfg5_s383_b128.json
+timeout 600 python tools/exp_latency.py > gpurun_out/r02_latency.log 2>&1
+cat gpurun_out/r02_latency.log
+timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_ops.py -m gpu -q -x -p no:cacheprovider -k "3x3_p1 or xcorr or 1x1_64_256" > gpurun_out/r02_sanitizer_memcheck_ops.txt 2>&1
+tail -4 gpurun_out/r02_sanitizer_memcheck_ops.txt
 timeout 1500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/r02_traffic.csv python bench.py --steps 6 --warmup 3 --min-seconds 0 --no-cpu --no-context --no-verify --no-loop > gpurun_out/r02_ncu_traffic.log 2>&1
 tail -1 gpurun_out/r02_ncu_traffic.log | cut -c1-150; wc -l gpurun_out/r02_traffic.csv
 timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"conv3x3_patch_kernel<64" -s 8 -c 2 -f -o gpurun_out/prof_patch64_r02 python bench.py --steps 2 --warmup 3 --min-seconds 0 --no-cpu --no-context --no-verify --no-loop > gpurun_out/r02_ncu_patch.log 2>&1
