@@ -22,24 +22,50 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; cannot build libsiammask_b200.so")
 
 
+HASH = LIB + ".srchash"
+
+
+def source_hash() -> str:
+    """sha256 over the sources, headers and compiler flags the library is built from (content, not mtimes: a snapshot
+    copy to another box shuffles the time stamps but not the bytes)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in SOURCES + HEADERS:
+        path = os.path.join(CSRC, d)
+        h.update(d.encode())
+        if os.path.exists(path):
+            with open(path, "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    try:
+        with open(HASH) as f:
+            return f.read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB + ".tmp", *[os.path.join(CSRC, s) for s in SOURCES]]
+    tmp = f"{LIB}.tmp{os.getpid()}"          # several ranks may build at once: private temp file, atomic replace
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", tmp, *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
+    digest = source_hash()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    os.replace(LIB + ".tmp", LIB)
+    os.replace(tmp, LIB)
+    with open(f"{HASH}.tmp{os.getpid()}", "w") as f:
+        f.write(digest + "\n")
+    os.replace(f"{HASH}.tmp{os.getpid()}", HASH)
     return LIB
 
 

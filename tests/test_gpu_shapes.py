@@ -209,3 +209,21 @@ def test_select_is_nan_safe(calib_sd):
     torch.cuda.synchronize()
     assert torch.isfinite(r).all()
     assert torch.equal(r, m.track_refine(torch.tensor([[0, 24], [24, 0]], dtype=torch.int32, device="cuda")))
+
+
+def test_step_graph_replay_matches_eager(calib_sd):
+    """`sm_step` under CUDA-graph replay (call 1 eager, call 2 captured, then replayed) == eager, fresh inputs honoured."""
+    B = 2
+    a, w, tsz = _consts(25, B)
+    ad, wd = torch.from_numpy(a).cuda(), torch.from_numpy(w.astype(np.float32)).cuda()
+    z, x1 = synthetic_inputs(76, B)
+    _, x2 = synthetic_inputs(77, B)
+    eager = _engine(calib_sd, max_batch=B)
+    graph = _engine(calib_sd, max_batch=B, graphs=True)
+    eager.template(z.cuda()); graph.template(z.cuda())
+    for it, xin in enumerate([x1, x2, x1, x2]):
+        t = torch.from_numpy(tsz + it)
+        oe = eager.step(xin.cuda(), ad, wd, t, PK, WI, refine=True, mask_head=False)
+        og = graph.step(xin.cuda(), ad, wd, t, PK, WI, refine=True, mask_head=False)
+        for k in ("cls", "loc", "pos", "records", "refine"):
+            assert torch.equal(oe[k], og[k]), f"call {it}: {k}"
