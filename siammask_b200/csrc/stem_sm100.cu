@@ -25,7 +25,8 @@ constexpr int STAGES = 4;
 constexpr int A_TILE = BM * BK * 2;        // 16 KB
 constexpr int B_TILE = BN * BK * 2;        // 8 KB
 constexpr int STG_TILE = 32 * 64;          // 32 rows x 32 cols fp16
-constexpr int NPROD = 128;
+constexpr int NPROD = 256;                 // two producer threads per tile row (each builds half of every k-block:
+                                           // the gather is a per-thread latency chain of 147 loads + conversions)
 constexpr int NEPI = 8;
 constexpr int NTHREADS = 64 + NPROD + 32 * NEPI;
 
@@ -51,12 +52,16 @@ struct SCfg {
 };
 
 // one 64-wide k-block of this thread's row: k = (r*7 + s)*3 + c
-template <int KB, int NSPLIT>
+// JH = which half of the k-block (4 of its 8 16-byte chunks) this thread builds; compile-time so that k -> (r, s, c)
+// folds into constant offsets
+template <int KB, int NSPLIT, int JH>
 __device__ __forceinline__ void build_kblock(const float* __restrict__ base, bool valid, int S, uint8_t* stage,
                                              int row) {
   uint8_t* rowp = stage + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int jj = 0; jj < 4; ++jj) {
+    constexpr int J0 = JH * 4;
+    const int j = J0 + jj;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -167,7 +172,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) stem_tc_kernel(const __grid_const
     }
   } else if (warp >= 2 && warp < 2 + NPROD / 32) {
     // ===================== A producers: one output pixel (tile row) per thread =====================
-    const int row = threadIdx.x - 64;
+    const int row = (threadIdx.x - 64) & (BM - 1);
+    const bool upper = threadIdx.x - 64 >= BM;          // warp-uniform: warps 2-5 build chunks 0-3, warps 6-9 chunks 4-7
     int stage = 0;
     uint32_t phase = 0;
     const int So2 = p.So * p.So;
@@ -181,7 +187,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) stem_tc_kernel(const __grid_const
       const float* base = p.x + ((size_t)b * 3 * p.S + 2 * y) * p.S + 2 * xo;
 #define SMK_STEM_KB(KB)                                                          \
   mbar_wait(&empty_bar[stage], phase ^ 1);                                       \
-  build_kblock<KB, NSPLIT>(base, valid, p.S, a_smem + stage * C::STAGE_BYTES, row); \
+  if (upper) build_kblock<KB, NSPLIT, 1>(base, valid, p.S, a_smem + stage * C::STAGE_BYTES, row); \
+  else build_kblock<KB, NSPLIT, 0>(base, valid, p.S, a_smem + stage * C::STAGE_BYTES, row); \
   fence_proxy_async();                                                           \
   mbar_arrive(&full_bar[stage]);                                                 \
   if (++stage == STAGES) { stage = 0; phase ^= 1; }
