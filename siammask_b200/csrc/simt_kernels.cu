@@ -5,6 +5,7 @@
 #include "common.cuh"
 
 #include <cmath>
+#include <type_traits>
 #include <cstdlib>
 #include <vector>
 
@@ -255,48 +256,107 @@ __global__ void __launch_bounds__(NTHREADS, 2) xcorr_nhwc_kernel(Act x, const __
     for (int v = 0; v < KW; ++v) kk[u][v] = split_load(k_hi, k_lo, (((size_t)b * KH + u) * KW + v) * out.C + c);
   __syncthreads();
   const int Ho = Hob, Wo = out.W, W = x.W;
+  // balanced task grid: row blocks of NR or NR-1 rows (25 -> 7,6,6,6), strips of SW or SW-1 columns; tasks are
+  // warp-uniform, and the four (rows, cols) shapes get their own straight-line code (no predicated-off FMAs)
   const int nrb = (Ho + NR - 1) / NR, nst = (Wo + SW - 1) / SW;
-  for (int task = warp; task < nrb * nst; task += NTHREADS / 32) {      // warp-uniform
+  const int r_base = Ho / nrb, r_extra = Ho % nrb, c_base = Wo / nst, c_extra = Wo % nst;   // first *_extra blocks get +1
+  __half* __restrict__ oh = out.hi;
+  __half* __restrict__ ol = out.lo;
+  const size_t pix_stride = out.C;
+  for (int task = warp; task < nrb * nst; task += NTHREADS / 32) {
     const int rb = task / nst, stp = task - rb * nst;
-    const int r0 = rb * NR, q0 = stp * SW;
-    const int nr = min(NR, Ho - r0), nc = min(SW, Wo - q0);
-    float acc[NR][SW];
-#pragma unroll
-    for (int i = 0; i < NR; ++i)
-#pragma unroll
-      for (int q = 0; q < SW; ++q) acc[i][q] = 0.f;
+    const int r0 = rb * r_base + min(rb, r_extra), q0 = stp * c_base + min(stp, c_extra);
+    const int nr = r_base + (rb < r_extra ? 1 : 0), nc = c_base + (stp < c_extra ? 1 : 0);
     const float* row = xs + ((size_t)r0 * W + q0) * XC_CH + lane;
+    const size_t obase = (((size_t)b * out.H + y0 + r0) * Wo + q0) * pix_stride + c;
+    auto run = [&](auto nr_tag, auto nc_tag) {
+      constexpr int NRr = decltype(nr_tag)::value, NCc = decltype(nc_tag)::value;
+      float acc[NRr][NCc];
 #pragma unroll
-    for (int r = 0; r < NR + KH - 1; ++r) {
-      if (r < nr + KH - 1) {
-        float xr[SW + KW - 1];
+      for (int i = 0; i < NRr; ++i)
 #pragma unroll
-        for (int q = 0; q < SW + KW - 1; ++q) xr[q] = q < nc + KW - 1 ? row[(r * W + q) * XC_CH] : 0.f;
+        for (int q = 0; q < NCc; ++q) acc[i][q] = 0.f;
+#pragma unroll
+      for (int r = 0; r < NRr + KH - 1; ++r) {
+        float xr[NCc + KW - 1];
+#pragma unroll
+        for (int q = 0; q < NCc + KW - 1; ++q) xr[q] = row[(r * W + q) * XC_CH];
 #pragma unroll
         for (int u = 0; u < KH; ++u) {
           const int i = r - u;
-          if (i >= 0 && i < NR && i < nr) {
+          if (i >= 0 && i < NRr) {
 #pragma unroll
-            for (int q = 0; q < SW; ++q)
+            for (int q = 0; q < NCc; ++q)
 #pragma unroll
               for (int v = 0; v < KW; ++v) acc[i][q] = fmaf(xr[q + v], kk[u][v], acc[i][q]);
           }
         }
       }
-    }
-    float amax = 0.f;
+      float amax = 0.f;
+      size_t orow = obase;
 #pragma unroll
-    for (int i = 0; i < NR; ++i)
-      if (i < nr) {
+      for (int i = 0; i < NRr; ++i) {
+        size_t o = orow;
 #pragma unroll
-        for (int q = 0; q < SW; ++q)
-          if (q < nc) {
-            const float v = acc[i][q] * mul;        // mul = 2^(s_corr - s_search - s_kernel): static activation scales
-            amax = fmaxf(amax, fabsf(v));
-            split_store(out.hi, out.lo, (((size_t)b * out.H + y0 + r0 + i) * Wo + q0 + q) * out.C + c, v);
-          }
+        for (int q = 0; q < NCc; ++q) {
+          const float v = acc[i][q] * mul;          // mul = 2^(s_corr - s_search - s_kernel): static activation scales
+          amax = fmaxf(amax, fabsf(v));
+          const __half hv = __float2half_rn(v);
+          oh[o] = hv;
+          if (ol != nullptr) ol[o] = __float2half_rn(v - __half2float(hv));
+          o += pix_stride;
+        }
+        orow += (size_t)Wo * pix_stride;
       }
-    flag_if_out_of_range(amax, ovf);
+      flag_if_out_of_range(amax, ovf);
+    };
+    using IR = std::integral_constant<int, NR>;
+    using IR1 = std::integral_constant<int, NR - 1>;
+    using IC = std::integral_constant<int, SW>;
+    using IC1 = std::integral_constant<int, SW - 1>;
+    if (nr == NR && nc == SW) run(IR{}, IC{});
+    else if (nr == NR && nc == SW - 1) run(IR{}, IC1{});
+    else if (nr == NR - 1 && nc == SW) run(IR1{}, IC{});
+    else if (nr == NR - 1 && nc == SW - 1) run(IR1{}, IC1{});
+    else {
+      // any other block shape (response sizes other than 25 / 41): predicated generic code
+      float acc[NR][SW];
+#pragma unroll
+      for (int i = 0; i < NR; ++i)
+#pragma unroll
+        for (int q = 0; q < SW; ++q) acc[i][q] = 0.f;
+#pragma unroll
+      for (int r = 0; r < NR + KH - 1; ++r) {
+        if (r < nr + KH - 1) {
+          float xr[SW + KW - 1];
+#pragma unroll
+          for (int q = 0; q < SW + KW - 1; ++q) xr[q] = q < nc + KW - 1 ? row[(r * W + q) * XC_CH] : 0.f;
+#pragma unroll
+          for (int u = 0; u < KH; ++u) {
+            const int i = r - u;
+            if (i >= 0 && i < NR && i < nr) {
+#pragma unroll
+              for (int q = 0; q < SW; ++q)
+#pragma unroll
+                for (int v = 0; v < KW; ++v) acc[i][q] = fmaf(xr[q + v], kk[u][v], acc[i][q]);
+            }
+          }
+        }
+      }
+      float amax = 0.f;
+#pragma unroll
+      for (int i = 0; i < NR; ++i)
+        if (i < nr) {
+#pragma unroll
+          for (int q = 0; q < SW; ++q)
+            if (q < nc) {
+              const float v = acc[i][q] * mul;
+              amax = fmaxf(amax, fabsf(v));
+              split_store(oh, ol, obase + ((size_t)i * Wo + q) * pix_stride, v);
+            }
+        }
+      flag_if_out_of_range(amax, ovf);
+    }
   }
 }
 
