@@ -124,8 +124,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
   // warp index through a shuffle: provably warp-uniform for the compiler, so the role branches below are convergent.
   // Every role loop is walked by its WHOLE warp and a single elected lane issues the TMA / tcgen05 instructions: their
   // operands live in uniform registers, and under a `threadIdx.x == k` branch ptxas wraps each of them in a
-  // divergence loop (ELECT / R2UR / BRA per instruction — ~90 clk of issue time per MMA, which capped the 128-wide
-  // exact tiles at ~65 % tensor duty in round 1).
+  // divergence loop (ELECT / R2UR / BRA per instruction — ~90 clk of issue time per MMA: slower than the 32..64 tensor
+  // clocks of an N = 64..128 MMA).
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const bool leader = elect_one();
