@@ -304,8 +304,24 @@ def run_gpu(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+
+    class _StdoutToStderr:
+        """NCCL writes its version banner to stdout when the first communicator comes up; the contract of this script
+        is ONE JSON line on stdout, so fd 1 points at stderr while the process group initialises."""
+        def __enter__(self):
+            sys.stdout.flush()
+            self.saved = os.dup(1)
+            os.dup2(2, 1)
+
+        def __exit__(self, *exc):
+            sys.stdout.flush()
+            os.dup2(self.saved, 1)
+            os.close(self.saved)
+
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        with _StdoutToStderr():
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
     S = args.search
     sharp = not args.rpn_only
     # weak scaling: args.batch streams per GPU; this rank owns a contiguous block of the global stream ids
@@ -321,8 +337,9 @@ def run_gpu(args, rank, local_rank, world):
         m.load_state_dict(sd)
     m.eval().to(dev)
     if world > 1:                       # the one collective of the whole job: weights, once, at init
-        broadcast_weights(m.weight_blob(), src=0)
-        torch.cuda.synchronize()
+        with _StdoutToStderr():
+            broadcast_weights(m.weight_blob(), src=0)
+            torch.cuda.synchronize()
         if rank != 0:
             m.adopt_weights()
     gen = torch.Generator(device=dev).manual_seed(100 + rank)

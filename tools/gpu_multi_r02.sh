@@ -11,7 +11,10 @@ run() {  # outfile bench-args...
   python - <<PY
 import json
 try:
-    d = json.load(open("gpurun_out/$out.json"))
+    txt = open("gpurun_out/$out.json").read()
+    line = [l for l in txt.splitlines() if l.startswith("{")][-1]
+    open("gpurun_out/$out.json", "w").write(line + "\n")
+    d = json.loads(line)
     print("$out", "N=", d["n_gpus"], round(d["value"]), "frames/s", round(d["ms_per_step"], 3), "ms/step; e2e", round(d["e2e"]["value"]),
           "; parity", d["parity_check"].get("max_rel_all_ranks", d["parity_check"]["max_rel"]), d["parity_check"].get("argmax_equal_all_ranks"))
 except Exception as e:
