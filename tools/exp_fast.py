@@ -1,7 +1,7 @@
 import sys, time, numpy as np, torch
 sys.path.insert(0, '.')
 import siammask_b200 as smb
-from siammask_b200 import tracker
+from siammask_b200 import anchors as tracker
 prec = sys.argv[1] if len(sys.argv) > 1 else 'fast'
 dev = torch.device('cuda', 0)
 B, S, R = 64, 255, 25
