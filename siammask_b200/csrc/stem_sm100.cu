@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) stem_tc_kernel(const __grid_const
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSPLIT; ++i) { tma_prefetch_desc(&p.tmB[i]); tma_prefetch_desc(&p.tmOut[i]); }
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], NPROD); mbar_init(&empty_bar[s], 1); }
+    // one arrival per producer WARP (after its lanes' fences): 256 single-thread arrivals serialise on the barrier word
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], NPROD / 32); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], NEPI); }
     mbar_init(b_bar, 1);
     fence_barrier_init();
@@ -190,7 +191,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) stem_tc_kernel(const __grid_const
   if (upper) build_kblock<KB, NSPLIT, 1>(base, valid, p.S, a_smem + stage * C::STAGE_BYTES, row); \
   else build_kblock<KB, NSPLIT, 0>(base, valid, p.S, a_smem + stage * C::STAGE_BYTES, row); \
   fence_proxy_async();                                                           \
-  mbar_arrive(&full_bar[stage]);                                                 \
+  __syncwarp();                                                                  \
+  if (lane == 0) mbar_arrive(&full_bar[stage]);                                  \
   if (++stage == STAGES) { stage = 0; phase ^= 1; }
       SMK_STEM_KB(0)
       SMK_STEM_KB(1)

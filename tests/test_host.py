@@ -29,6 +29,35 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in _lib.load().sm_version()
 
 
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of the C-ABI structs (sm_config, sm_tensor_desc, sm_step_io, sm_tracker_hp) against what a C
+    compiler makes of include/siammask_b200.h: sizes and field offsets."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    structs = {"sm_config": _lib.SmConfig, "sm_tensor_desc": _lib.SmTensorDesc, "sm_step_io": _lib.SmStepIO,
+               "sm_tracker_hp": _lib.SmTrackerHp}
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "siammask_b200.h"', "int main(void) {"]
+    for cname, ct in structs.items():
+        prog.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            prog.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        prog.append('  printf("\\n");')
+    prog += ["  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "abi"
+    subprocess.run([cc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    for line in filter(None, out):
+        name, size, *offs = line.split()
+        ct = structs[name]
+        assert int(size) == C.sizeof(ct), name
+        assert [int(o) for o in offs] == [getattr(ct, f).offset for f, _ in ct._fields_], name
+
+
 def test_checkpoint_contract():
     keys = expected_keys()
     assert len(keys) == 303                         # 356 state tensors minus 53 num_batches_tracked
