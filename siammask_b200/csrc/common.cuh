@@ -70,6 +70,7 @@ struct GemmParams {
   int n_tiles, m_tiles;
   int staged;           // 1: epilogue goes smem -> TMA store (NHWC split outputs)
   int reverse_m;        // 1: walk the M tiles from the last to the first (see Engine::conv_into: L2 reuse)
+  int ncat;             // 1: exact mode issues A_hi x [B_hi; B_lo] as ONE MMA of N = 2*BLOCK_N (A_hi read from smem once)
   Epilogue ep;
 };
 

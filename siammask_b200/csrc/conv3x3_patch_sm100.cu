@@ -50,6 +50,7 @@ struct PatchParams {
   int tiles_per_img, num_tiles;
   int panel_bytes;         // one plane of one patch buffer incl. slack rows
   int patch_rows;          // (RO+2)*PW
+  int ncat;                // 1: hi*hi and hi*lo as ONE MMA of N = 2*CM over [B_hi; B_lo] (see conv_gemm_sm100.cu)
   Epilogue ep;
 };
 
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv3x3_patch_kernel(const __gri
   using C = PCfg<CM, NSPLIT>;
   constexpr int NKB = C::NKB;
   constexpr uint32_t idesc = umma_idesc_f16(128, CM);
+  constexpr uint32_t idesc_cat = umma_idesc_f16(128, NSPLIT == 2 ? 2 * CM : CM);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // layout: patch buffer 0 | patch buffer 1 (each NSPLIT panels) | B ring | barriers
@@ -198,15 +200,27 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv3x3_patch_kernel(const __gri
           const uint64_t db_hi = umma_desc_kmajor<128>(b_hi);
           const uint64_t db_lo = umma_desc_kmajor<128>(b_hi + C::B_TILE_BYTES);
           if (leader) {
+            if (NSPLIT == 2 && p.ncat != 0) {
+              // the lo weight tile follows the hi tile in the stage and the accumulators are adjacent TMEM columns:
+              // the shifted A_hi view crosses the smem port once for hi*hi and hi*lo together
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t kadd = static_cast<uint64_t>(k * 2);   // 32 bytes >> 4 in the start-address field
-              umma_f16(tmem_d, da_hi + kadd, db_hi + kadd, idesc, acc_main);
-              acc_main = 1;
-              if constexpr (NSPLIT == 2) {
-                umma_f16(tmem_d + CM, da_lo + kadd, db_hi + kadd, idesc, acc_lo);
-                acc_lo = 1;
-                umma_f16(tmem_d + CM, da_hi + kadd, db_lo + kadd, idesc, 1u);
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t kadd = static_cast<uint64_t>(k * 2);
+                umma_f16(tmem_d, da_hi + kadd, db_hi + kadd, idesc_cat, acc_main);
+                acc_main = 1;
+                umma_f16(tmem_d + CM, da_lo + kadd, db_hi + kadd, idesc, 1u);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t kadd = static_cast<uint64_t>(k * 2);   // 32 bytes >> 4 in the start-address field
+                umma_f16(tmem_d, da_hi + kadd, db_hi + kadd, idesc, acc_main);
+                acc_main = 1;
+                if constexpr (NSPLIT == 2) {
+                  umma_f16(tmem_d + CM, da_lo + kadd, db_hi + kadd, idesc, acc_lo);
+                  acc_lo = 1;
+                  umma_f16(tmem_d + CM, da_hi + kadd, db_lo + kadd, idesc, 1u);
+                }
               }
             }
             umma_commit(&bempty[bstage]);
@@ -357,6 +371,8 @@ void launch_conv3x3_patch(const Act& in, const ConvGeom& g, const __half* w_hi, 
   p.patch_rows = (p.RO + 2) * p.PW;
   p.panel_bytes = (p.patch_rows + 2 * P_SLACK_ROWS) * 128;
   SMK_CHECK(p.panel_bytes % 1024 == 0, "patch panels must keep the 1024-byte swizzle alignment");
+  static const int no_ncat = [] { const char* e = getenv("SMB200_NO_NCAT"); return e ? atoi(e) : 0; }();
+  p.ncat = no_ncat == 0 ? 1 : 0;
   p.ep = ep;
   for (int s = 0; s < nsplit; ++s) {
     const __half* a = s == 0 ? in.hi : in.lo;

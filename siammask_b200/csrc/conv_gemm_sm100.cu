@@ -251,6 +251,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
   } else if (warp == 1 && rank == 0) {
     // ===================== MMA issuer (pairs: the leader CTA issues for both) =====================
     constexpr uint32_t idesc = umma_idesc_f16(BLOCK_M * CG, BLOCK_N);
+    constexpr bool NCAT_OK = NSPLIT == 2 && CG == 1 && 2 * BLOCK_N <= 256;
+    constexpr uint32_t idesc_cat = umma_idesc_f16(BLOCK_M, NCAT_OK ? 2 * BLOCK_N : BLOCK_N);
     auto wait_bar = [&](uint64_t* bar, uint32_t parity) {
       if constexpr (CG == 2) mbar_wait_guarded(bar, parity);
       else mbar_wait(bar, parity);
@@ -290,15 +292,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
           const uint64_t da_lo0 = umma_desc_kmajor<C::SWIZZLE>(a_hi + A_TILE_BYTES);
           const uint64_t db_lo0 = umma_desc_kmajor<C::SWIZZLE>(b_hi + C::B_TILE_BYTES);
           if (leader) {
+            if (NCAT_OK && p.ncat != 0 && !ident) {
+              // The B_lo tile follows the B_hi tile in the stage, so [B_hi; B_lo] is one K-major operand of 2*BLOCK_N
+              // rows and the two accumulators are adjacent TMEM columns: A_hi x [B_hi; B_lo] is ONE MMA (hi*hi ->
+              // acc0, hi*lo -> acc1) and A_hi crosses the shared-memory port once instead of twice (operand reads
+              // per k-block 96 -> 80 KB at 128 x 128).  Both accumulate flags are always equal (set together).
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              const uint64_t kadd = static_cast<uint64_t>(k * UMMA_K * 2 / 16);
-              mma(tmem_d, da_hi0 + kadd, db_hi0 + kadd, acc_main);
-              acc_main = 1;
-              if constexpr (NSPLIT == 2) {
-                mma(tmem_d + BLOCK_N, da_lo0 + kadd, db_hi0 + kadd, acc_lo);
-                acc_lo = 1;
-                if (!ident) mma(tmem_d + BLOCK_N, da_hi0 + kadd, db_lo0 + kadd, 1u);
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                const uint64_t kadd = static_cast<uint64_t>(k * UMMA_K * 2 / 16);
+                umma_f16(tmem_d, da_hi0 + kadd, db_hi0 + kadd, idesc_cat, acc_main);
+                acc_main = 1;
+                mma(tmem_d + BLOCK_N, da_lo0 + kadd, db_hi0 + kadd, 1u);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                const uint64_t kadd = static_cast<uint64_t>(k * UMMA_K * 2 / 16);
+                mma(tmem_d, da_hi0 + kadd, db_hi0 + kadd, acc_main);
+                acc_main = 1;
+                if constexpr (NSPLIT == 2) {
+                  mma(tmem_d + BLOCK_N, da_lo0 + kadd, db_hi0 + kadd, acc_lo);
+                  acc_lo = 1;
+                  if (!ident) mma(tmem_d + BLOCK_N, da_hi0 + kadd, db_lo0 + kadd, 1u);
+                }
               }
             }
             commit(&empty_bar[stage]);                                   // smem slot free once these MMAs retire
@@ -836,6 +852,9 @@ void launch_gemm_multi(const GemmInput* convs, int nconv, const Act* residual, i
   p.n_tiles = cout_pad / block_n;
   p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   p.reverse_m = reverse_m ? 1 : 0;
+  // SMB200_NO_NCAT=1: issue hi*hi and hi*lo as two MMAs again (A/B runs)
+  static const int no_ncat = [] { const char* e = getenv("SMB200_NO_NCAT"); return e ? atoi(e) : 0; }();
+  p.ncat = (nsplit == 2 && cg == 1 && 2 * block_n <= 256 && no_ncat == 0) ? 1 : 0;
   p.nseg = 0;
   for (int i = 0; i < nconv; ++i) {
     const ConvGeom& g = convs[i].g;

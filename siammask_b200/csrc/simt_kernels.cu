@@ -484,6 +484,7 @@ __global__ void gather_mask_col_kernel(const float* __restrict__ mask, const int
 // ConvTranspose2d(256, 32, 15, 15) on a 1x1 input (custom.py:120,149) == [B x Cin] x [Cin x N] + bias,
 // N = 15*15*32 ordered (y, x, co) so the result is NHWC fp32.  Thread = output column n, 8 samples.
 constexpr int DC_BT = 8;
+constexpr int DC_KU = 16;   // weight loads in flight per thread
 __global__ void __launch_bounds__(256) deconv_kernel(const float* __restrict__ p3, const float* __restrict__ w,
                                                      const float* __restrict__ bias, float* __restrict__ out,
                                                      int B, int Cin, int N, int cout) {
@@ -499,7 +500,18 @@ __global__ void __launch_bounds__(256) deconv_kernel(const float* __restrict__ p
   float acc[DC_BT];
 #pragma unroll
   for (int t = 0; t < DC_BT; ++t) acc[t] = 0.f;
-  for (int k = 0; k < Cin; ++k) {
+  // the weight column is a strided walk through 7 MB (one L2 round trip per element): keep DC_KU loads in flight
+  int k = 0;
+  for (; k + DC_KU <= Cin; k += DC_KU) {
+    float wv[DC_KU];
+#pragma unroll
+    for (int u = 0; u < DC_KU; ++u) wv[u] = __ldg(w + (size_t)(k + u) * N + n);
+#pragma unroll
+    for (int u = 0; u < DC_KU; ++u)
+#pragma unroll
+      for (int t = 0; t < DC_BT; ++t) acc[t] = fmaf(sp3[t * Cin + k + u], wv[u], acc[t]);
+  }
+  for (; k < Cin; ++k) {
     const float wv = __ldg(w + (size_t)k * N + n);
 #pragma unroll
     for (int t = 0; t < DC_BT; ++t) acc[t] = fmaf(sp3[t * Cin + k], wv, acc[t]);
