@@ -217,9 +217,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv3x3_patch_kernel(const __gri
                 umma_f16(tmem_d, da_hi + kadd, db_hi + kadd, idesc, acc_main);
                 acc_main = 1;
                 if constexpr (NSPLIT == 2) {
-                  umma_f16(tmem_d + CM, da_lo + kadd, db_hi + kadd, idesc, acc_lo);
+                  umma_f16(tmem_d + CM, da_hi + kadd, db_lo + kadd, idesc, acc_lo);   // order of the concatenated form
                   acc_lo = 1;
-                  umma_f16(tmem_d + CM, da_hi + kadd, db_lo + kadd, idesc, 1u);
+                  umma_f16(tmem_d + CM, da_lo + kadd, db_hi + kadd, idesc, 1u);
                 }
               }
             }

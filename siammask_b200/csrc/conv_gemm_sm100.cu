@@ -311,9 +311,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
                 mma(tmem_d, da_hi0 + kadd, db_hi0 + kadd, acc_main);
                 acc_main = 1;
                 if constexpr (NSPLIT == 2) {
+                  // same order as the concatenated form (hi*lo, then lo*hi): every tile variant rounds identically
+                  if (!ident) {
+                    mma(tmem_d + BLOCK_N, da_hi0 + kadd, db_lo0 + kadd, acc_lo);
+                    acc_lo = 1;
+                  }
                   mma(tmem_d + BLOCK_N, da_lo0 + kadd, db_hi0 + kadd, acc_lo);
                   acc_lo = 1;
-                  if (!ident) mma(tmem_d + BLOCK_N, da_hi0 + kadd, db_lo0 + kadd, 1u);
                 }
               }
             }

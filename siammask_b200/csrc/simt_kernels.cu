@@ -665,7 +665,8 @@ __global__ void __launch_bounds__(256) small_conv3x3_kernel(const float* __restr
 // the penalty is evaluated in fp64 (numpy promotes those expressions to float64 through the float64 target size).
 // np.argmax semantics incl. NaN: the first NaN wins over every number (a NaN/Inf network output or a 0/0 target
 // size must not leave `besti` unset: rec/pos are always in range).  rec[7] = best index (exact in fp32).
-__global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ cls, const float* __restrict__ loc,
+constexpr int SEL_THREADS = 512;   // latency-bound (fp64 exp / divides per candidate): more threads, fewer serial candidates each
+__global__ void __launch_bounds__(SEL_THREADS) select_kernel(const float* __restrict__ cls, const float* __restrict__ loc,
                                                      const float* __restrict__ anchors,
                                                      const float* __restrict__ window,
                                                      const double* __restrict__ tsz, int A, int R, double penalty_k,
@@ -708,14 +709,14 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ c
     const int isn = ps != ps ? 1 : 0;
     if (better(isn, ps, idx, bestnan, best, besti)) { best = ps; besti = idx; bestnan = isn; }
   }
-  __shared__ double sv[256];
-  __shared__ int si[256];
-  __shared__ int sn[256];
+  __shared__ double sv[SEL_THREADS];
+  __shared__ int si[SEL_THREADS];
+  __shared__ int sn[SEL_THREADS];
   sv[threadIdx.x] = best;
   si[threadIdx.x] = besti;
   sn[threadIdx.x] = bestnan;
   __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
+  for (int s = SEL_THREADS / 2; s > 0; s >>= 1) {
     if (threadIdx.x < s) {
       if (better(sn[threadIdx.x + s], sv[threadIdx.x + s], si[threadIdx.x + s], sn[threadIdx.x], sv[threadIdx.x],
                  si[threadIdx.x])) {
@@ -1167,7 +1168,7 @@ void launch_warp_affine(const float* src, int sh, int sw, const double* maps, fl
 void launch_select(const float* cls, const float* loc, const float* anchors, const float* window, const double* tsz,
                    int B, int A, int R, double penalty_k, double window_influence, int32_t* best_idx, int32_t* pos,
                    float* rec, cudaStream_t st) {
-  select_kernel<<<B, 256, 0, st>>>(cls, loc, anchors, window, tsz, A, R, penalty_k, window_influence, best_idx, pos, rec);
+  select_kernel<<<B, SEL_THREADS, 0, st>>>(cls, loc, anchors, window, tsz, A, R, penalty_k, window_influence, best_idx, pos, rec);
   SMK_CUDA(cudaGetLastError());
 }
 
