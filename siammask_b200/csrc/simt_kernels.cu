@@ -482,44 +482,62 @@ __global__ void gather_mask_col_kernel(const float* __restrict__ mask, const int
 }
 
 // ConvTranspose2d(256, 32, 15, 15) on a 1x1 input (custom.py:120,149) == [B x Cin] x [Cin x N] + bias,
-// N = 15*15*32 ordered (y, x, co) so the result is NHWC fp32.  Thread = output column n, 8 samples.
-constexpr int DC_BT = 8;
-constexpr int DC_KU = 16;   // weight loads in flight per thread
-__global__ void __launch_bounds__(256) deconv_kernel(const float* __restrict__ p3, const float* __restrict__ w,
-                                                     const float* __restrict__ bias, float* __restrict__ out,
-                                                     int B, int Cin, int N, int cout) {
-  extern __shared__ float sp3[];   // [DC_BT][Cin]
+// N = 15*15*32 ordered (y, x, co) so the result is NHWC fp32.  A thread walks one weight column — a strided walk through
+// 7 MB, one DRAM round trip per element, and ptxas keeps only 3-4 of the unrolled loads in flight — so the kernel lasts
+// as long as ONE thread's chain: a block is 64 columns x 4 K-slices (chains of Cin/4), 8 samples per thread, partial sums
+// reduced through shared memory in a fixed order.
+constexpr int DC_BT = 8;      // samples per block
+constexpr int DC_COLS = 64;   // output columns per block
+constexpr int DC_KS = 4;      // K slices per block
+constexpr int DC_KU = 16;     // unrolled weight loads per slice step
+__global__ void __launch_bounds__(DC_COLS * DC_KS) deconv_kernel(const float* __restrict__ p3, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, float* __restrict__ out,
+                                                                 int B, int Cin, int N, int cout) {
+  extern __shared__ float sp3[];             // [DC_BT][Cin], then red[DC_KS][DC_BT][DC_COLS]
+  float* red = sp3 + DC_BT * Cin;
   const int b0 = blockIdx.y * DC_BT;
   for (int i = threadIdx.x; i < DC_BT * Cin; i += blockDim.x) {
     const int bb = b0 + i / Cin;
     sp3[i] = bb < B ? p3[(size_t)bb * Cin + i % Cin] : 0.f;
   }
   __syncthreads();
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+  const int c = threadIdx.x % DC_COLS, ks = threadIdx.x / DC_COLS;
+  const int n = blockIdx.x * DC_COLS + c;
+  const int nl = n < N ? n : N - 1;          // columns past the end: load a valid one, never stored
+  const int kspan = (Cin + DC_KS - 1) / DC_KS;
+  const int k0 = ks * kspan, k1 = min(Cin, k0 + kspan);
   float acc[DC_BT];
 #pragma unroll
   for (int t = 0; t < DC_BT; ++t) acc[t] = 0.f;
-  // the weight column is a strided walk through 7 MB (one L2 round trip per element): keep DC_KU loads in flight
-  int k = 0;
-  for (; k + DC_KU <= Cin; k += DC_KU) {
+  int k = k0;
+  for (; k + DC_KU <= k1; k += DC_KU) {
     float wv[DC_KU];
 #pragma unroll
-    for (int u = 0; u < DC_KU; ++u) wv[u] = __ldg(w + (size_t)(k + u) * N + n);
+    for (int u = 0; u < DC_KU; ++u) wv[u] = __ldg(w + (size_t)(k + u) * N + nl);
 #pragma unroll
     for (int u = 0; u < DC_KU; ++u)
 #pragma unroll
       for (int t = 0; t < DC_BT; ++t) acc[t] = fmaf(sp3[t * Cin + k + u], wv[u], acc[t]);
   }
-  for (; k < Cin; ++k) {
-    const float wv = __ldg(w + (size_t)k * N + n);
+  for (; k < k1; ++k) {
+    const float wv = __ldg(w + (size_t)k * N + nl);
 #pragma unroll
     for (int t = 0; t < DC_BT; ++t) acc[t] = fmaf(sp3[t * Cin + k], wv, acc[t]);
   }
-  const float bv = bias[n % cout];
 #pragma unroll
-  for (int t = 0; t < DC_BT; ++t)
-    if (b0 + t < B) out[(size_t)(b0 + t) * N + n] = acc[t] + bv;
+  for (int t = 0; t < DC_BT; ++t) red[(ks * DC_BT + t) * DC_COLS + c] = acc[t];
+  __syncthreads();
+  if (n >= N) return;
+  const float bv = bias[n % cout];
+  // slice ks finishes samples ks*2, ks*2+1 (DC_BT / DC_KS each): sum of the K slices in slice order
+#pragma unroll
+  for (int j = 0; j < DC_BT / DC_KS; ++j) {
+    const int t = ks * (DC_BT / DC_KS) + j;
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < DC_KS; ++q) v += red[(q * DC_BT + t) * DC_COLS + c];
+    if (b0 + t < B) out[(size_t)(b0 + t) * N + n] = v + bv;
+  }
 }
 
 // max |hi| of a split-plane activation (calibration of the static activation scales): float bits are monotone for
@@ -1137,8 +1155,10 @@ void launch_gather_mask_col(const float* mask, const int32_t* pos, int B, int C,
 
 void launch_deconv(const float* p3, const float* w, const float* bias, float* out, int B, int Cin, int N, int cout,
                    cudaStream_t st) {
-  dim3 grid((N + 255) / 256, (B + DC_BT - 1) / DC_BT);
-  deconv_kernel<<<grid, 256, DC_BT * Cin * sizeof(float), st>>>(p3, w, bias, out, B, Cin, N, cout);
+  dim3 grid((N + DC_COLS - 1) / DC_COLS, (B + DC_BT - 1) / DC_BT);
+  const size_t smem = (size_t)(DC_BT * Cin + DC_KS * DC_BT * DC_COLS) * sizeof(float);
+  SMK_CHECK(smem <= 48 * 1024, "deconv: Cin too large for the staged samples");
+  deconv_kernel<<<grid, DC_COLS * DC_KS, smem, st>>>(p3, w, bias, out, B, Cin, N, cout);
   SMK_CUDA(cudaGetLastError());
 }
 

@@ -1,6 +1,6 @@
 """Small-batch latency of one whole frame (sm_step: track_mask + selection + refine), eager vs CUDA-graph replay,
 plus the host time of the call itself (enqueue only).  Used for profiles/r02_other_configs.md."""
-import sys, time, numpy as np, torch
+import os, sys, time, numpy as np, torch
 sys.path.insert(0, '.')
 import siammask_b200 as smb
 from siammask_b200 import anchors as anc
@@ -8,8 +8,9 @@ dev = torch.device('cuda', 0)
 R = 25
 anchors_dev = torch.from_numpy(anc.generate_anchor(smb.DEFAULT_ANCHORS, R)).to(dev)
 window_dev = torch.from_numpy(anc.cosine_window(R, 5).astype(np.float32)).to(dev)
-for prec in ('exact', 'fast'):
-  for B in (1, 8):
+ONLY = os.environ.get("SMB200_LAT_ONLY", "")          # "exact1": exact mode, B=1 only (short GPU calls)
+for prec in (('exact',) if ONLY == "exact1" else ('exact', 'fast')):
+  for B in ((1,) if ONLY == "exact1" else (1, 8)):
    for graphs in (False, True):
     m = smb.Custom(anchors=smb.DEFAULT_ANCHORS, max_batch=B, num_slots=B, precision=prec, graphs=graphs).load_state_dict(smb.synthetic_state_dict(0)).eval().to(dev)
     gen = torch.Generator(device=dev).manual_seed(1)
